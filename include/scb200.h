@@ -1,0 +1,109 @@
+/* scb200.h -- C ABI of the B200-native batched big-integer engine for the DGK/Veugen secure comparison.
+ *
+ * The reference (tno.mpc.protocols.secure_comparison 4.4.0) has no FFI: its hot path is reached through
+ * Python operator overloading on Paillier/DGK ciphertext objects which end in gmpy2.powmod / gmpy2.invert
+ * (GMP mpz_powm / mpz_invert / mpz_mul+mpz_mod).  Every entry point below names the reference interface
+ * it replaces (file:line under /root/reference/src/tno/mpc/protocols/secure_comparison/).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative SCB_E* code and never throws;
+ *     scb_last_error(ctx) gives the message of the last failure on that context.
+ *   - big integers are little-endian arrays of uint32_t words ("limbs"), least significant word first;
+ *     a batch is a C-contiguous [B][k] array.  The caller owns every buffer; outputs are written into
+ *     caller-provided buffers; no pointer returned by the library outlives its context.
+ *   - "_dev" variants take DEVICE pointers (same layouts) and enqueue on the context's stream without
+ *     synchronising (scb_sync waits); the others take HOST pointers and are synchronous.
+ *   - one context per GPU; a context is not re-entrant.  Work is independent per batch element, so
+ *     multi-GPU use is one context (and one host thread or process) per device on a slice of the batch.
+ *   - results are canonical residues in [0, modulus), bit-identical to what GMP / CPython return.
+ */
+#ifndef SCB200_H
+#define SCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scb_ctx scb_ctx;
+
+enum {
+  SCB_OK = 0,
+  SCB_EINVAL = -1,   /* bad argument (null pointer, even modulus, size out of range, unknown slot) */
+  SCB_ECUDA = -2,    /* CUDA runtime error (message in scb_last_error) */
+  SCB_ENOMEM = -3,   /* device or host allocation failed */
+  SCB_ENOTINV = -4,  /* at least one element had no modular inverse (per-element flags tell which) */
+  SCB_ESTATE = -5    /* keys / tables required by the call have not been loaded */
+};
+
+/* Modulus slots.  SCB_MOD_USER0.. are free for the generic primitives; the others are filled by the
+ * key-loading calls below. */
+enum {
+  SCB_MOD_PAILLIER_N2 = 0, /* N^2  : Paillier ciphertext space (paillier.public_key.n_squared) */
+  SCB_MOD_PAILLIER_N = 1,  /* N    : Paillier plaintext space */
+  SCB_MOD_DGK_N = 2,       /* n    : DGK ciphertext space (dgk.public_key.n) */
+  SCB_MOD_DGK_P = 3,       /* p    : DGK secret prime (dgk.secret_key.p), is_zero test */
+  SCB_MOD_PAILLIER_P2 = 4, /* p^2  : CRT half of KeyHolder-side Paillier work */
+  SCB_MOD_PAILLIER_Q2 = 5, /* q^2 */
+  SCB_MOD_PAILLIER_P = 6,  /* p */
+  SCB_MOD_PAILLIER_Q = 7,  /* q */
+  SCB_MOD_USER0 = 8,
+  SCB_MOD_SLOTS = 16
+};
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int scb_ctx_create(int device_ordinal, scb_ctx** out);
+void scb_ctx_destroy(scb_ctx* ctx);
+const char* scb_last_error(const scb_ctx* ctx);
+int scb_sync(scb_ctx* ctx);                       /* wait for everything enqueued by *_dev calls */
+void* scb_stream(scb_ctx* ctx);                   /* the context's cudaStream_t (for event timing) */
+int scb_version(void);
+/* number of kernels launched by this context since creation (bench.py reports it as gpu_launches) */
+unsigned long long scb_launch_count(const scb_ctx* ctx);
+/* pinned host memory for callers that want DMA-able staging buffers */
+int scb_host_alloc(size_t bytes, void** out);
+int scb_host_free(void* ptr);
+
+/* ---- generic batched primitives -------------------------------------------------------------------
+ * Replace tno.mpc.encryption_schemes.utils.pow_mod / mod_inv -> gmpy2.powmod / gmpy2.invert and the
+ * mulmod inside every scheme.add.                                      */
+
+/* Load an odd modulus of k32 words into a slot (Montgomery constants are derived on the host). */
+int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k32);
+
+/* out[i] = base[i] ^ exp[i] mod n.   base: [B][k32]; exp: [B][exp_words] or, when exp_shared != 0, a
+ * single [exp_words] exponent used for every element; exp_bits = number of significant exponent bits
+ * to scan (the same for all elements; higher bits must be zero).  mul_in (nullable, [B][k32]):
+ * out[i] = mul_in[i] * base[i]^exp[i] mod n -- the "randomize" fusion c * rho^N mod N^2
+ * (initiator.py:109, keyholder.py:126-128).                                                          */
+int scb_modexp(scb_ctx* ctx, int slot, const uint32_t* base, const uint32_t* exp, int exp_words, int exp_shared,
+               int exp_bits, const uint32_t* mul_in, uint32_t* out, size_t B);
+int scb_modexp_dev(scb_ctx* ctx, int slot, const uint32_t* base, const uint32_t* exp, int exp_words, int exp_shared,
+                   int exp_bits, const uint32_t* mul_in, uint32_t* out, size_t B);
+
+/* out[i] = a[i] * b[i] mod n  (scheme.add on raw ciphertext values). */
+int scb_modmul(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B);
+int scb_modmul_dev(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B);
+
+/* out[i] = a[i]^-1 mod n  (scheme.neg).  ok[i] = 1 when the inverse exists, else 0 and out[i] = 0
+ * (GMP mpz_invert returns 0; gmpy2 / CPython raise ZeroDivisionError / ValueError).  Returns
+ * SCB_ENOTINV when any element failed (all other elements are still valid).                          */
+int scb_modinv(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+int scb_modinv_dev(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+
+/* Fixed-base exponentiation with a precomputed 8-bit window table: out[i] = mul_in[i] * base^exp[i].
+ * scb_fixed_base_load builds the table for `base` (k32 words) and exponents of at most exp_bits bits
+ * in table slot `tslot` (0..3) over modulus slot `slot`.  This is DGK's randomizer h^rho
+ * (keyholder.py:106-108, initiator.py:153-154).                                                      */
+int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint32_t* base, int exp_bits);
+int scb_fixed_base_exp(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
+                       uint32_t* out, size_t B);
+int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
+                           uint32_t* out, size_t B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB200_H */

@@ -1,0 +1,54 @@
+// host_ctx.hpp -- the opaque scb_ctx behind the C ABI (one per GPU; owns all device memory).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace scb {
+struct ModulusDev;
+struct KeysDev;
+}  // namespace scb
+
+struct scb_ctx {
+  static constexpr int NSCRATCH = 8;
+  static constexpr int NFB = 4;
+
+  struct Mod {
+    scb::ModulusDev* dev = nullptr;
+    int K = 0, k32 = 0, bits = 0;
+    bool loaded = false;
+    std::vector<uint32_t> words;
+  };
+  struct FixedBase {
+    uint32_t* table = nullptr;   // [nwin][256][K] Montgomery digits
+    int nwin = 0, slot = -1, exp_bits = 0;
+    bool loaded = false;
+  };
+
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  unsigned long long launches = 0;
+  Mod mod[16];
+  FixedBase fb[NFB];
+  void* scratch_ptr[NSCRATCH] = {nullptr};
+  size_t scratch_bytes[NSCRATCH] = {0};
+  std::map<const void*, int> occupancy_cache;
+  scb::KeysDev* keys_dev = nullptr;   // protocol-level key material (kernels_protocol.cuh)
+  std::vector<uint8_t> keys_host;     // host mirror of KeysDev
+
+  int scratch(int which, size_t bytes, void** out);
+  int grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block);
+  int launched(const char* what);
+};
+
+namespace scb {
+int fail(scb_ctx* ctx, int code, const char* fmt, ...);
+int cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what);
+int config_K_for_bits(int bits);
+int modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+}  // namespace scb

@@ -1,0 +1,291 @@
+// kernels_generic.cuh -- batched modexp / modmul / fixed-base / modinv kernels on top of bn29.cuh.
+#pragma once
+#include "bn29.cuh"
+
+namespace scb {
+
+constexpr int BLOCK_THREADS = 128;
+constexpr int WARPS_PER_BLOCK = BLOCK_THREADS / 32;
+
+template <int L, int TPI>
+struct GroupIndex {
+  static constexpr int GPW = Geo<L, TPI>::GPW;
+  static constexpr int GROUPS_PER_BLOCK = GPW * WARPS_PER_BLOCK;
+  __device__ static __forceinline__ size_t slot() {   // global group slot of this lane's group
+    return (static_cast<size_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * GPW + (threadIdx.x & 31) / TPI;
+  }
+  __device__ static __forceinline__ size_t total() { return static_cast<size_t>(gridDim.x) * GROUPS_PER_BLOCK; }
+  __device__ static __forceinline__ uint32_t* warp_smem(uint32_t* smem) {
+    return smem + (threadIdx.x >> 5) * Geo<L, TPI>::WARP_SMEM_WORDS;
+  }
+};
+
+// bits [pos, pos+w) of a little-endian word array (w <= 8), zero beyond `words`
+__device__ __forceinline__ uint32_t get_bits(const uint32_t* __restrict__ e, int words, int pos, int w) {
+  const int i = pos >> 5, sh = pos & 31;
+  const uint32_t lo = (i < words) ? __ldg(e + i) : 0u;
+  const uint32_t hi = (i + 1 < words) ? __ldg(e + i + 1) : 0u;
+  return __funnelshift_r(lo, hi, sh) & ((1u << w) - 1u);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fixed-window Montgomery exponentiation for ONE group: acc = x~^e (Montgomery form, lazy).
+// xm, acc: K-digit slots; table: (1<<wbits) slots.  All in this group's global scratch.
+// -------------------------------------------------------------------------------------------------
+template <int L, int TPI>
+__device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* xm, const uint32_t* __restrict__ e,
+                                             int ewords, int ebits, int wbits, uint32_t* table) {
+  constexpr int K = Geo<L, TPI>::K;
+  const int nwin = (ebits + wbits - 1) / wbits;
+  if (nwin == 0) {
+    copy_digits(g, acc, g.m->one);
+    return;
+  }
+  // table[0] = 1~, table[1] = x~, table[v] = table[v-1] * x~
+  copy_digits(g, table, g.m->one);
+  copy_digits(g, table + K, xm);
+  for (int v = 2; v < (1 << wbits); v++) mm<L, TPI>(g.m, g.sm, table + static_cast<size_t>(v) * K, table + static_cast<size_t>(v - 1) * K, xm);
+  uint32_t win = get_bits(e, ewords, (nwin - 1) * wbits, wbits);
+  const uint32_t* cur = table + static_cast<size_t>(win) * K;   // first squaring reads the table entry directly
+  if (nwin == 1) {
+    copy_digits(g, acc, cur);
+    return;
+  }
+  for (int i = nwin - 2; i >= 0; i--) {
+    for (int s = 0; s < wbits; s++) {
+      mm<L, TPI>(g.m, g.sm, acc, cur, cur);
+      cur = acc;
+    }
+    win = get_bits(e, ewords, i * wbits, wbits);
+    mm<L, TPI>(g.m, g.sm, acc, acc, table + static_cast<size_t>(win) * K);
+  }
+}
+
+// scratch slots of one group in k_modexp: X, ACC, TMP, then the window table
+template <int L, int TPI>
+__host__ __device__ constexpr size_t modexp_scratch_words(int wbits) {
+  return static_cast<size_t>(Geo<L, TPI>::K) * (3 + (static_cast<size_t>(1) << wbits));
+}
+
+// out[i] = (mul_in[i] *) base[i]^exp[i] mod n
+template <int L, int TPI>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp,
+         int ewords, size_t exp_stride, int ebits, int wbits, uint32_t* scratch, const uint32_t* __restrict__ mul_in,
+         uint32_t* __restrict__ out, int kout, size_t B) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  uint32_t* X = scratch + slot * modexp_scratch_words<L, TPI>(wbits);
+  uint32_t* ACC = X + K;
+  uint32_t* TMP = ACC + K;
+  uint32_t* table = TMP + K;
+  const size_t rounds = (B + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t inst = rd * total + slot;
+    const bool active = inst < B;
+    if (!active) inst = B - 1;
+    words_to_digits(g, TMP, base + inst * kbase, kbase);
+    mm<L, TPI>(m, g.sm, X, TMP, m->r2);                         // x~ = x*R
+    group_modexp(g, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
+    if (mul_in != nullptr) {
+      words_to_digits(g, TMP, mul_in + inst * kout, kout);
+      mm<L, TPI>(m, g.sm, TMP, TMP, m->r2);
+      mm<L, TPI>(m, g.sm, ACC, ACC, TMP);
+    }
+    mm<L, TPI>(m, g.sm, TMP, ACC, m->unit);                     // leave Montgomery form
+    canonical_store(g, TMP, out + inst * kout, kout, active);
+  }
+}
+
+// out[i] = a[i] * b[i] mod n   (a_stride / b_stride = 0 broadcasts one operand)
+template <int L, int TPI>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+k_modmul(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ a, size_t a_stride, const uint32_t* __restrict__ b,
+         size_t b_stride, int k32, uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  uint32_t* A = scratch + slot * 2 * K;
+  uint32_t* Bv = A + K;
+  const size_t rounds = (B + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t inst = rd * total + slot;
+    const bool active = inst < B;
+    if (!active) inst = B - 1;
+    words_to_digits(g, A, a + inst * a_stride, k32);
+    words_to_digits(g, Bv, b + inst * b_stride, k32);
+    mm<L, TPI>(m, g.sm, A, A, m->r2);                            // a*R
+    mm<L, TPI>(m, g.sm, A, A, Bv);                               // a*R*b/R = a*b
+    canonical_store(g, A, out + inst * k32, k32, active);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fixed-base tables: T[j][v] = base^(v * 256^j) in Montgomery form, j < nwin, v < 256.
+// -------------------------------------------------------------------------------------------------
+// step 1 (one group): T[j][1] for all j by repeated squaring.
+template <int L, int TPI>
+__global__ void __launch_bounds__(32) k_fb_bases(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, int k32,
+                                                  uint32_t* table, int nwin) {
+  extern __shared__ uint32_t smem[];
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, smem);
+  // every group of the warp computes the same thing into its own scratch copy; group 0's copy is the
+  // table itself.  (Keeps all 32 lanes converged for mm's shuffles without special cases.)
+  const int grp = (threadIdx.x & 31) / TPI;
+  uint32_t* T = table + (grp == 0 ? 0 : static_cast<size_t>(nwin) * 256 * K + static_cast<size_t>(grp - 1) * K * 2);
+  // group 0 writes T[j][1]; the other groups ping-pong in two private slots behind the table
+  uint32_t* cur = (grp == 0) ? T + K : T;
+  words_to_digits(g, cur, base, k32);
+  mm<L, TPI>(m, g.sm, cur, cur, m->r2);
+  for (int j = 1; j < nwin; j++) {
+    uint32_t* nxt = (grp == 0) ? table + (static_cast<size_t>(j) * 256 + 1) * K : (cur == T ? T + K : T);
+    mm<L, TPI>(m, g.sm, nxt, cur, cur);
+    for (int s = 1; s < 8; s++) mm<L, TPI>(m, g.sm, nxt, nxt, nxt);
+    cur = nxt;
+  }
+}
+
+// step 2 (one group per window j): T[j][0] = 1~, T[j][v] = T[j][v-1] * T[j][1].
+template <int L, int TPI>
+__global__ void __launch_bounds__(BLOCK_THREADS) k_fb_fill(const ModulusDev* __restrict__ m, uint32_t* table, int nwin, uint32_t* dump) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t j = GI::slot();
+  const bool active = j < static_cast<size_t>(nwin);
+  // inactive groups recompute window 0 into a private dump area (keeps the warp converged)
+  uint32_t* T = active ? table + j * 256 * K : dump + (j - nwin) * 2 * K;
+  const uint32_t* base1 = active ? T + K : table + K;
+  if (active) copy_digits(g, T, m->one);
+  const uint32_t* prev = base1;
+  for (int v = 2; v < 256; v++) {
+    uint32_t* dst = active ? T + static_cast<size_t>(v) * K : T + (v & 1) * K;
+    mm<L, TPI>(m, g.sm, dst, prev, base1);
+    prev = dst;
+  }
+}
+
+// acc (Montgomery, lazy) *= base^exp using the 8-bit window table.  e: this group's exponent words.
+template <int L, int TPI>
+__device__ __forceinline__ void group_fixed_base_mul(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* table, int nwin,
+                                                     const uint32_t* __restrict__ e, int ewords) {
+  constexpr int K = Geo<L, TPI>::K;
+  for (int j = 0; j < nwin; j++) {
+    const uint32_t v = get_bits(e, ewords, j * 8, 8);
+    mm<L, TPI>(g.m, g.sm, acc, acc, table + (static_cast<size_t>(j) * 256 + v) * K);
+  }
+}
+
+template <int L, int TPI>
+__global__ void __launch_bounds__(BLOCK_THREADS)
+k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, const uint32_t* __restrict__ exp, int ewords,
+             const uint32_t* __restrict__ mul_in, uint32_t* scratch, uint32_t* __restrict__ out, int k32, size_t B) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  uint32_t* ACC = scratch + slot * K;
+  const size_t rounds = (B + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t inst = rd * total + slot;
+    const bool active = inst < B;
+    if (!active) inst = B - 1;
+    if (mul_in != nullptr) {
+      words_to_digits(g, ACC, mul_in + inst * k32, k32);
+      mm<L, TPI>(m, g.sm, ACC, ACC, m->r2);
+    } else {
+      copy_digits(g, ACC, m->one);
+    }
+    group_fixed_base_mul(g, ACC, table, nwin, exp + inst * ewords, ewords);
+    mm<L, TPI>(m, g.sm, ACC, ACC, m->unit);
+    canonical_store(g, ACC, out + inst * k32, k32, active);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Modular inverse, one thread per element, binary extended Euclid on 32-bit words in local memory.
+// Invariants: x1*a = u, x2*a = v (mod n); v stays odd.  Not on the throughput-critical path: the
+// protocol kernels batch their inversions with Montgomery's trick so this runs once per ~64 values.
+// -------------------------------------------------------------------------------------------------
+constexpr int INV_MAXW = 260;
+
+__device__ __forceinline__ bool w_is_zero(const uint32_t* x, int k) {
+  for (int i = 0; i < k; i++)
+    if (x[i]) return false;
+  return true;
+}
+__device__ __forceinline__ bool w_less(const uint32_t* x, const uint32_t* y, int k) {
+  for (int i = k - 1; i >= 0; i--)
+    if (x[i] != y[i]) return x[i] < y[i];
+  return false;
+}
+__device__ __forceinline__ uint32_t w_sub(uint32_t* x, const uint32_t* y, int k) {   // x -= y, returns borrow
+  uint32_t borrow = 0;
+  for (int i = 0; i < k; i++) {
+    const uint64_t d = static_cast<uint64_t>(x[i]) - y[i] - borrow;
+    x[i] = static_cast<uint32_t>(d);
+    borrow = static_cast<uint32_t>(d >> 63);
+  }
+  return borrow;
+}
+__device__ __forceinline__ uint32_t w_add(uint32_t* x, const uint32_t* y, int k) {   // x += y, returns carry
+  uint32_t carry = 0;
+  for (int i = 0; i < k; i++) {
+    const uint64_t s = static_cast<uint64_t>(x[i]) + y[i] + carry;
+    x[i] = static_cast<uint32_t>(s);
+    carry = static_cast<uint32_t>(s >> 32);
+  }
+  return carry;
+}
+__device__ __forceinline__ void w_shr1(uint32_t* x, int k, uint32_t top_in) {
+  for (int i = 0; i < k - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+  x[k - 1] = (x[k - 1] >> 1) | (top_in << 31);
+}
+
+__global__ void __launch_bounds__(64) k_modinv(const uint32_t* __restrict__ n, int k, const uint32_t* __restrict__ a,
+                                               uint32_t* __restrict__ out, uint8_t* __restrict__ ok, size_t B) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= B) return;
+  uint32_t bufU[INV_MAXW], bufV[INV_MAXW], bufX1[INV_MAXW], bufX2[INV_MAXW];
+  uint32_t *u = bufU, *v = bufV, *x1 = bufX1, *x2 = bufX2;
+  for (int i = 0; i < k; i++) {
+    u[i] = a[idx * k + i];
+    v[i] = n[i];
+    x1[i] = 0;
+    x2[i] = 0;
+  }
+  x1[0] = 1;
+  // reduce a below n if needed (inputs are residues, but stay safe): a >= n -> a -= n while possible
+  for (int guard = 0; guard < 4 && !w_less(u, v, k); guard++) w_sub(u, v, k);
+  while (!w_is_zero(u, k)) {
+    while ((u[0] & 1u) == 0) {
+      w_shr1(u, k, 0);
+      if (x1[0] & 1u) {
+        const uint32_t carry = w_add(x1, n, k);
+        w_shr1(x1, k, carry);
+      } else {
+        w_shr1(x1, k, 0);
+      }
+    }
+    if (w_less(u, v, k)) {
+      uint32_t* t = u; u = v; v = t;
+      t = x1; x1 = x2; x2 = t;
+    }
+    w_sub(u, v, k);
+    if (w_sub(x1, x2, k)) w_add(x1, n, k);       // x1 = (x1 - x2) mod n
+  }
+  bool one = v[0] == 1;
+  for (int i = 1; i < k && one; i++) one = v[i] == 0;
+  for (int i = 0; i < k; i++) out[idx * k + i] = one ? x2[i] : 0u;
+  ok[idx] = one ? 1 : 0;
+}
+
+}  // namespace scb

@@ -1,0 +1,549 @@
+// scb200.cu -- host side of the C ABI declared in include/scb200.h (context, modulus constants,
+// launch geometry) for the sm_100a kernels in kernels_generic.cuh / kernels_protocol.cuh.
+#include "../../../include/scb200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_ctx.hpp"
+#include "kernels_generic.cuh"
+
+using namespace scb;
+
+// -------------------------------------------------------------------------------------------------
+// small host-side big-integer helpers (only used once per modulus, for the Montgomery constants)
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+typedef std::vector<uint32_t> Words;
+
+int words_bits(const Words& x) {
+  for (int i = static_cast<int>(x.size()) - 1; i >= 0; i--)
+    if (x[i]) return i * 32 + 32 - __builtin_clz(x[i]);
+  return 0;
+}
+bool words_geq(const Words& a, const Words& b) {   // same length
+  for (int i = static_cast<int>(a.size()) - 1; i >= 0; i--)
+    if (a[i] != b[i]) return a[i] > b[i];
+  return true;
+}
+void words_sub(Words& a, const Words& b) {
+  uint64_t borrow = 0;
+  for (size_t i = 0; i < a.size(); i++) {
+    const uint64_t d = static_cast<uint64_t>(a[i]) - b[i] - borrow;
+    a[i] = static_cast<uint32_t>(d);
+    borrow = (d >> 63) & 1u;
+  }
+}
+// x = 2x mod n   (x < n; arrays have one spare top word)
+void words_dbl_mod(Words& x, const Words& n) {
+  uint32_t carry = 0;
+  for (size_t i = 0; i < x.size(); i++) {
+    const uint32_t nc = x[i] >> 31;
+    x[i] = (x[i] << 1) | carry;
+    carry = nc;
+  }
+  if (words_geq(x, n)) words_sub(x, n);
+}
+void words_to_digits(const Words& x, uint32_t* digits, int K) {
+  for (int d = 0; d < K; d++) {
+    const int bit = d * W, w = bit >> 5, sh = bit & 31;
+    uint64_t v = (static_cast<size_t>(w) < x.size()) ? x[w] : 0u;
+    if (static_cast<size_t>(w + 1) < x.size()) v |= static_cast<uint64_t>(x[w + 1]) << 32;
+    digits[d] = static_cast<uint32_t>(v >> sh) & DMASK;
+  }
+}
+
+}  // namespace
+
+int scb::config_K_for_bits(int bits) {
+  // R = 2^(29K) must exceed 4n; supported (L, TPI) products
+  static const int Ks[] = {36, 54, 72, 108, 144, 216, 288};
+  for (int K : Ks)
+    if (29 * K >= bits + 2) return K;
+  return -1;
+}
+
+int scb::fail(scb_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    ctx->error = buf;
+  }
+  return code;
+}
+
+int scb::cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, e == cudaErrorMemoryAllocation ? SCB_ENOMEM : SCB_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int scb_ctx::scratch(int which, size_t bytes, void** out) {
+  if (which < 0 || which >= NSCRATCH) return fail(this, SCB_EINVAL, "bad scratch index");
+  if (scratch_bytes[which] < bytes) {
+    if (scratch_ptr[which]) {
+      cudaStreamSynchronize(stream);
+      cudaFree(scratch_ptr[which]);
+      scratch_ptr[which] = nullptr;
+      scratch_bytes[which] = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&scratch_ptr[which], want);
+    if (e != cudaSuccess) return cuda_fail(this, e, "cudaMalloc(scratch)");
+    scratch_bytes[which] = want;
+  }
+  *out = scratch_ptr[which];
+  return SCB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------------
+extern "C" int scb_version(void) { return 100; }
+
+extern "C" int scb_ctx_create(int device, scb_ctx** out) {
+  if (!out) return SCB_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) return SCB_ECUDA;
+  scb_ctx* ctx = new scb_ctx();
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
+    delete ctx;
+    return SCB_ECUDA;
+  }
+  *out = ctx;
+  return SCB_OK;
+}
+
+extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& m : ctx->mod)
+    if (m.dev) cudaFree(m.dev);
+  for (auto& t : ctx->fb)
+    if (t.table) cudaFree(t.table);
+  for (int i = 0; i < scb_ctx::NSCRATCH; i++)
+    if (ctx->scratch_ptr[i]) cudaFree(ctx->scratch_ptr[i]);
+  if (ctx->keys_dev) cudaFree(ctx->keys_dev);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* scb_last_error(const scb_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+extern "C" void* scb_stream(scb_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+extern "C" unsigned long long scb_launch_count(const scb_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+extern "C" int scb_sync(scb_ctx* ctx) {
+  if (!ctx) return SCB_EINVAL;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+  return SCB_OK;
+}
+
+extern "C" int scb_host_alloc(size_t bytes, void** out) {
+  if (!out) return SCB_EINVAL;
+  return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? SCB_OK : SCB_ENOMEM;
+}
+extern "C" int scb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SCB_OK : SCB_ECUDA; }
+
+// -------------------------------------------------------------------------------------------------
+// modulus constants
+// -------------------------------------------------------------------------------------------------
+extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k32) {
+  if (!ctx || !n || slot < 0 || slot >= SCB_MOD_SLOTS || k32 <= 0 || k32 > INV_MAXW - 2) return fail(ctx, SCB_EINVAL, "scb_modulus_load: bad argument");
+  if ((n[0] & 1u) == 0) return fail(ctx, SCB_EINVAL, "scb_modulus_load: modulus must be odd");
+  Words nn(n, n + k32);
+  const int bits = words_bits(nn);
+  if (bits < 2) return fail(ctx, SCB_EINVAL, "scb_modulus_load: modulus too small");
+  const int K = config_K_for_bits(bits);
+  if (K < 0) return fail(ctx, SCB_EINVAL, "scb_modulus_load: %d-bit modulus exceeds the supported 8350 bits", bits);
+  cudaSetDevice(ctx->device);
+  ModulusDev h;
+  memset(&h, 0, sizeof(h));
+  h.K = K;
+  h.k32 = k32;
+  h.bits = bits;
+  // n' = -n^-1 mod 2^29 (Newton on 32 bits)
+  uint32_t inv = n[0];
+  for (int i = 0; i < 5; i++) inv *= 2u - n[0] * inv;
+  h.np = (0u - inv) & DMASK;
+  Words nw(nn);
+  nw.push_back(0);
+  words_to_digits(nw, h.n, K);
+  h.unit[0] = 1;
+  // x = 2^(bits-1) mod n = 2^(bits-1) (< n), then double up to 2^(29K), 2^(58K), 2^(87K)
+  Words x(k32 + 1, 0);
+  x[(bits - 1) >> 5] = 1u << ((bits - 1) & 31);
+  int e = bits - 1;
+  const int targets[3] = {W * K, 2 * W * K, 3 * W * K};
+  uint32_t* dst[3] = {h.one, h.r2, h.r3};
+  for (int t = 0; t < 3; t++) {
+    for (; e < targets[t]; e++) words_dbl_mod(x, nw);
+    words_to_digits(x, dst[t], K);
+  }
+  scb_ctx::Mod& md = ctx->mod[slot];
+  if (!md.dev) {
+    cudaError_t ce = cudaMalloc(&md.dev, sizeof(ModulusDev));
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaMalloc(modulus)");
+  }
+  cudaError_t ce = cudaMemcpyAsync(md.dev, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "upload modulus");
+  md.K = K;
+  md.k32 = k32;
+  md.bits = bits;
+  md.words.assign(n, n + k32);
+  md.loaded = true;
+  return SCB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// launch helpers
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+int window_bits_for(int ebits) {
+  if (ebits <= 6) return 1;
+  if (ebits <= 24) return 2;
+  if (ebits <= 80) return 3;
+  if (ebits <= 240) return 4;
+  if (ebits <= 1100) return 5;
+  return 6;
+}
+
+template <int L, int TPI>
+int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, const uint32_t* exp, int ewords, size_t estride, int ebits,
+                  const uint32_t* mul_in, uint32_t* out, size_t B) {
+  using G = Geo<L, TPI>;
+  const int wbits = window_bits_for(ebits);
+  const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_modexp<L, TPI>), smem, B, gpb);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * modexp_scratch_words<L, TPI>(wbits) * sizeof(uint32_t), &scratch);
+  if (rc) return rc;
+  k_modexp<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, base, md.k32, exp, ewords, estride, ebits, wbits,
+                                                               static_cast<uint32_t*>(scratch), mul_in, out, md.k32, B);
+  return ctx->launched("k_modexp");
+}
+
+template <int L, int TPI>
+int launch_modmul(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* a, size_t as, const uint32_t* b, size_t bs, uint32_t* out, size_t B) {
+  using G = Geo<L, TPI>;
+  const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_modmul<L, TPI>), smem, B, gpb);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * 2 * G::K * sizeof(uint32_t), &scratch);
+  if (rc) return rc;
+  k_modmul<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, a, as, b, bs, md.k32, static_cast<uint32_t*>(scratch), out, B);
+  return ctx->launched("k_modmul");
+}
+
+template <int L, int TPI>
+int launch_fb_build(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base_dev, uint32_t* table, int nwin) {
+  using G = Geo<L, TPI>;
+  k_fb_bases<L, TPI><<<1, 32, sizeof(uint32_t) * G::WARP_SMEM_WORDS, ctx->stream>>>(md.dev, base_dev, md.k32, table, nwin);
+  int rc = ctx->launched("k_fb_bases");
+  if (rc) return rc;
+  const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
+  k_fb_fill<L, TPI><<<(nwin + gpb - 1) / gpb, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, table, nwin,
+                                                                                table + static_cast<size_t>(nwin) * 256 * G::K);
+  return ctx->launched("k_fb_fill");
+}
+
+template <int L, int TPI>
+int launch_fixed_base(scb_ctx* ctx, const scb_ctx::Mod& md, const scb_ctx::FixedBase& fb, const uint32_t* exp, int ewords,
+                      const uint32_t* mul_in, uint32_t* out, size_t B) {
+  using G = Geo<L, TPI>;
+  const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_fixed_base<L, TPI>), smem, B, gpb);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * G::K * sizeof(uint32_t), &scratch);
+  if (rc) return rc;
+  k_fixed_base<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, fb.table, fb.nwin, exp, ewords, mul_in,
+                                                                   static_cast<uint32_t*>(scratch), out, md.k32, B);
+  return ctx->launched("k_fixed_base");
+}
+
+}  // namespace
+
+#define SCB_DISPATCH_K(K, CALL)                                                   \
+  switch (K) {                                                                    \
+    case 36: return CALL(18, 2);                                                  \
+    case 54: return CALL(27, 2);                                                  \
+    case 72: return CALL(18, 4);                                                  \
+    case 108: return CALL(27, 4);                                                 \
+    case 144: return CALL(18, 8);                                                 \
+    case 216: return CALL(27, 8);                                                 \
+    case 288: return CALL(18, 16);                                                \
+    default: return fail(ctx, SCB_EINVAL, "unsupported digit count %d", K);       \
+  }
+
+int scb_ctx::grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block) {
+  auto it = occupancy_cache.find(kernel);
+  int per_sm;
+  if (it == occupancy_cache.end()) {
+    per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    occupancy_cache[kernel] = per_sm;
+  } else {
+    per_sm = it->second;
+  }
+  const size_t need = (B + groups_per_block - 1) / groups_per_block;
+  const size_t cap = static_cast<size_t>(per_sm) * num_sms;
+  return static_cast<int>(std::max<size_t>(1, std::min(need, cap)));
+}
+
+int scb_ctx::launched(const char* what) {
+  launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(this, e, what);
+  return SCB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic primitives, device-pointer versions
+// -------------------------------------------------------------------------------------------------
+static int check_mod(scb_ctx* ctx, int slot, const char* who) {
+  if (!ctx) return SCB_EINVAL;
+  if (slot < 0 || slot >= SCB_MOD_SLOTS) return fail(ctx, SCB_EINVAL, "%s: bad modulus slot %d", who, slot);
+  if (!ctx->mod[slot].loaded) return fail(ctx, SCB_ESTATE, "%s: modulus slot %d not loaded", who, slot);
+  cudaSetDevice(ctx->device);
+  return SCB_OK;
+}
+
+extern "C" int scb_modexp_dev(scb_ctx* ctx, int slot, const uint32_t* base, const uint32_t* exp, int exp_words, int exp_shared,
+                              int exp_bits, const uint32_t* mul_in, uint32_t* out, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modexp");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!base || !exp || !out || exp_words <= 0 || exp_bits < 0 || exp_bits > exp_words * 32) return fail(ctx, SCB_EINVAL, "scb_modexp: bad argument");
+  const scb_ctx::Mod& md = ctx->mod[slot];
+  const size_t estride = exp_shared ? 0 : static_cast<size_t>(exp_words);
+#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, exp, exp_words, estride, exp_bits, mul_in, out, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
+extern "C" int scb_modmul_dev(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modmul");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!a || !b || !out) return fail(ctx, SCB_EINVAL, "scb_modmul: null pointer");
+  const scb_ctx::Mod& md = ctx->mod[slot];
+#define CALL(L, TPI) launch_modmul<L, TPI>(ctx, md, a, md.k32, b, md.k32, out, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
+int scb::modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B) {
+  const scb_ctx::Mod& md = ctx->mod[slot];
+  void* nwords = nullptr;
+  int rc = ctx->scratch(1, sizeof(uint32_t) * md.k32, &nwords);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(nwords, md.words.data(), sizeof(uint32_t) * md.k32, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "upload modulus words");
+  k_modinv<<<static_cast<unsigned>((B + 63) / 64), 64, 0, ctx->stream>>>(static_cast<const uint32_t*>(nwords), md.k32, a, out, ok, B);
+  return ctx->launched("k_modinv");
+}
+
+extern "C" int scb_modinv_dev(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modinv");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!a || !out || !ok) return fail(ctx, SCB_EINVAL, "scb_modinv: null pointer");
+  return modinv_dev_raw(ctx, slot, a, out, ok, B);
+}
+
+extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint32_t* base, int exp_bits) {
+  int rc = check_mod(ctx, slot, "scb_fixed_base_load");
+  if (rc) return rc;
+  if (tslot < 0 || tslot >= scb_ctx::NFB || !base || exp_bits <= 0 || exp_bits > 8192) return fail(ctx, SCB_EINVAL, "scb_fixed_base_load: bad argument");
+  const scb_ctx::Mod& md = ctx->mod[slot];
+  scb_ctx::FixedBase& fb = ctx->fb[tslot];
+  const int nwin = (exp_bits + 7) / 8;
+  // + a tail of 128 two-slot private areas used by the surplus groups of the build kernels
+  const size_t bytes = (static_cast<size_t>(nwin) * 256 + 256) * md.K * sizeof(uint32_t);
+  if (fb.table) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(fb.table);
+    fb.table = nullptr;
+  }
+  cudaError_t e = cudaMalloc(&fb.table, bytes);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(fixed-base table)");
+  void* bdev = nullptr;
+  rc = ctx->scratch(1, sizeof(uint32_t) * md.k32, &bdev);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(bdev, base, sizeof(uint32_t) * md.k32, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "upload fixed base");
+  fb.nwin = nwin;
+  fb.slot = slot;
+  fb.exp_bits = exp_bits;
+  uint32_t* table = fb.table;
+  const uint32_t* bd = static_cast<const uint32_t*>(bdev);
+#define CALL(L, TPI) launch_fb_build<L, TPI>(ctx, md, bd, table, nwin)
+  auto run = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
+#undef CALL
+  rc = run();
+  if (rc) return rc;
+  rc = scb_sync(ctx);
+  if (rc) return rc;
+  fb.loaded = true;
+  return SCB_OK;
+}
+
+extern "C" int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
+                                      uint32_t* out, size_t B) {
+  if (!ctx) return SCB_EINVAL;
+  if (tslot < 0 || tslot >= scb_ctx::NFB || !ctx->fb[tslot].loaded) return fail(ctx, SCB_ESTATE, "scb_fixed_base_exp: table %d not loaded", tslot);
+  const scb_ctx::FixedBase& fb = ctx->fb[tslot];
+  if (B == 0) return SCB_OK;
+  if (!exp || !out || exp_words <= 0 || exp_words * 32 > fb.nwin * 8 + 31) return fail(ctx, SCB_EINVAL, "scb_fixed_base_exp: exponent of %d words exceeds the table (%d bits)", exp_words, fb.exp_bits);
+  cudaSetDevice(ctx->device);
+  const scb_ctx::Mod& md = ctx->mod[fb.slot];
+#define CALL(L, TPI) launch_fixed_base<L, TPI>(ctx, md, fb, exp, exp_words, mul_in, out, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-pointer wrappers: stage through device scratch, run, copy back, synchronise
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct Staging {
+  scb_ctx* ctx;
+  int rc = SCB_OK;
+  size_t offset = 0;
+  char* base = nullptr;
+  explicit Staging(scb_ctx* c, size_t total_bytes) : ctx(c) {
+    void* p = nullptr;
+    rc = ctx->scratch(2, total_bytes + 4096, &p);
+    base = static_cast<char*>(p);
+  }
+  template <typename T>
+  T* reserve(size_t count) {
+    T* p = reinterpret_cast<T*>(base + offset);
+    offset += (count * sizeof(T) + 255) & ~static_cast<size_t>(255);
+    return p;
+  }
+  template <typename T>
+  T* upload(const T* host, size_t count) {
+    if (!host) return nullptr;
+    T* p = reserve<T>(count);
+    if (rc == SCB_OK) {
+      cudaError_t e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "H2D copy");
+    }
+    return p;
+  }
+  template <typename T>
+  void download(T* host, const T* dev, size_t count) {
+    if (rc == SCB_OK) {
+      cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "D2H copy");
+    }
+  }
+};
+inline size_t pad256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
+
+}  // namespace
+
+extern "C" int scb_modexp(scb_ctx* ctx, int slot, const uint32_t* base, const uint32_t* exp, int exp_words, int exp_shared,
+                          int exp_bits, const uint32_t* mul_in, uint32_t* out, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modexp");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!base || !exp || !out || exp_words <= 0) return fail(ctx, SCB_EINVAL, "scb_modexp: bad argument");
+  const size_t k = ctx->mod[slot].k32, ne = exp_shared ? exp_words : B * exp_words;
+  Staging st(ctx, 3 * pad256(B * k * 4) + pad256(ne * 4));
+  if (st.rc) return st.rc;
+  const uint32_t* dbase = st.upload(base, B * k);
+  const uint32_t* dexp = st.upload(exp, ne);
+  const uint32_t* dmul = st.upload(mul_in, B * k);
+  uint32_t* dout = st.reserve<uint32_t>(B * k);
+  if (st.rc) return st.rc;
+  rc = scb_modexp_dev(ctx, slot, dbase, dexp, exp_words, exp_shared, exp_bits, dmul, dout, B);
+  if (rc) return rc;
+  st.download(out, dout, B * k);
+  if (st.rc) return st.rc;
+  return scb_sync(ctx);
+}
+
+extern "C" int scb_modmul(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modmul");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!a || !b || !out) return fail(ctx, SCB_EINVAL, "scb_modmul: null pointer");
+  const size_t k = ctx->mod[slot].k32;
+  Staging st(ctx, 3 * pad256(B * k * 4));
+  if (st.rc) return st.rc;
+  const uint32_t* da = st.upload(a, B * k);
+  const uint32_t* db = st.upload(b, B * k);
+  uint32_t* dout = st.reserve<uint32_t>(B * k);
+  if (st.rc) return st.rc;
+  rc = scb_modmul_dev(ctx, slot, da, db, dout, B);
+  if (rc) return rc;
+  st.download(out, dout, B * k);
+  if (st.rc) return st.rc;
+  return scb_sync(ctx);
+}
+
+extern "C" int scb_modinv(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B) {
+  int rc = check_mod(ctx, slot, "scb_modinv");
+  if (rc) return rc;
+  if (B == 0) return SCB_OK;
+  if (!a || !out || !ok) return fail(ctx, SCB_EINVAL, "scb_modinv: null pointer");
+  const size_t k = ctx->mod[slot].k32;
+  Staging st(ctx, 2 * pad256(B * k * 4) + pad256(B));
+  if (st.rc) return st.rc;
+  const uint32_t* da = st.upload(a, B * k);
+  uint32_t* dout = st.reserve<uint32_t>(B * k);
+  uint8_t* dok = st.reserve<uint8_t>(B);
+  if (st.rc) return st.rc;
+  rc = scb_modinv_dev(ctx, slot, da, dout, dok, B);
+  if (rc) return rc;
+  st.download(out, dout, B * k);
+  st.download(ok, dok, B);
+  if (st.rc) return st.rc;
+  rc = scb_sync(ctx);
+  if (rc) return rc;
+  for (size_t i = 0; i < B; i++)
+    if (!ok[i]) return fail(ctx, SCB_ENOTINV, "scb_modinv: element %zu has no inverse", i);
+  return SCB_OK;
+}
+
+extern "C" int scb_fixed_base_exp(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
+                                  uint32_t* out, size_t B) {
+  if (!ctx) return SCB_EINVAL;
+  if (tslot < 0 || tslot >= scb_ctx::NFB || !ctx->fb[tslot].loaded) return fail(ctx, SCB_ESTATE, "scb_fixed_base_exp: table %d not loaded", tslot);
+  if (B == 0) return SCB_OK;
+  if (!exp || !out || exp_words <= 0) return fail(ctx, SCB_EINVAL, "scb_fixed_base_exp: bad argument");
+  cudaSetDevice(ctx->device);
+  const size_t k = ctx->mod[ctx->fb[tslot].slot].k32;
+  Staging st(ctx, 2 * pad256(B * k * 4) + pad256(B * exp_words * 4));
+  if (st.rc) return st.rc;
+  const uint32_t* dexp = st.upload(exp, B * exp_words);
+  const uint32_t* dmul = st.upload(mul_in, B * k);
+  uint32_t* dout = st.reserve<uint32_t>(B * k);
+  if (st.rc) return st.rc;
+  int rc = scb_fixed_base_exp_dev(ctx, tslot, dexp, exp_words, dmul, dout, B);
+  if (rc) return rc;
+  st.download(out, dout, B * k);
+  if (st.rc) return st.rc;
+  return scb_sync(ctx);
+}

@@ -1,0 +1,171 @@
+"""Engine: one CUDA context (one GPU) of the batched big-integer engine, generic primitives.
+
+Thin, typed Python over the C ABI (include/scb200.h).  Host entry points take/return numpy ``uint32``
+limb arrays (``[B][k]``, little-endian); ``*_dev`` entry points take device tensors (anything with
+``data_ptr()``, e.g. ``torch.uint8/int32`` tensors viewed as 32-bit words) and only enqueue work.
+
+These primitives stand where the reference calls ``tno.mpc.encryption_schemes.utils.pow_mod`` /
+``mod_inv`` (-> ``gmpy2.powmod`` / ``gmpy2.invert``) and the modular product inside ``scheme.add``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _native as nat
+from .limbs import int_to_limbs, limbs_for_bits
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[scb {code}] {message}")
+        self.code = code
+
+
+class NotInvertibleError(ZeroDivisionError):
+    """An element had no modular inverse (gmpy2 raises ZeroDivisionError, CPython ValueError)."""
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = nat.load_library()
+        handle = ctypes.c_void_p()
+        rc = self.lib.scb_ctx_create(device, ctypes.byref(handle))
+        if rc != nat.SCB_OK or not handle.value:
+            raise EngineError(rc, f"cannot create a CUDA context on device {device} (no GPU visible? there is no CPU fallback)")
+        self.ctx = handle
+        self.device = device
+        self._moduli: dict[int, tuple[int, int]] = {}   # slot -> (modulus, k32)
+        self._fixed_base: dict[int, tuple[int, int]] = {}  # tslot -> (slot, exp_bits)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self) -> None:
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.scb_ctx_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc == nat.SCB_OK:
+            return
+        msg = self.lib.scb_last_error(self.ctx).decode(errors="replace")
+        if rc == nat.SCB_ENOTINV:
+            raise NotInvertibleError(msg)
+        if rc == nat.SCB_EINVAL:
+            raise ValueError(msg)
+        raise EngineError(rc, msg)
+
+    def sync(self) -> None:
+        self._check(self.lib.scb_sync(self.ctx))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.scb_stream(self.ctx) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.scb_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ moduli
+    def load_modulus(self, slot: int, modulus: int, k32: Optional[int] = None) -> int:
+        """Load an odd modulus; returns the limb count ``k32`` every operand of this slot must have."""
+        if modulus % 2 == 0 or modulus < 3:
+            raise ValueError("modulus must be odd and >= 3")
+        k = k32 if k32 is not None else limbs_for_bits(modulus.bit_length())
+        words = int_to_limbs(modulus, k)
+        self._check(self.lib.scb_modulus_load(self.ctx, slot, nat._ptr(words), k))
+        self._moduli[slot] = (modulus, k)
+        return k
+
+    def modulus(self, slot: int) -> int:
+        return self._moduli[slot][0]
+
+    def k32(self, slot: int) -> int:
+        return self._moduli[slot][1]
+
+    # ------------------------------------------------------------------ host-buffer primitives
+    def modexp(self, slot: int, base: np.ndarray, exp: np.ndarray, exp_bits: Optional[int] = None,
+               mul_in: Optional[np.ndarray] = None) -> np.ndarray:
+        """``out[i] = (mul_in[i] *) base[i] ** exp[i] mod n``.  ``exp``: ``[B][ew]`` or shared ``[ew]``."""
+        k = self.k32(slot)
+        base = nat._host_u32(base)
+        if base.ndim != 2 or base.shape[1] != k:
+            raise ValueError(f"base must be [B][{k}]")
+        B = base.shape[0]
+        exp = nat._host_u32(exp)
+        shared = exp.ndim == 1
+        ew = exp.shape[-1]
+        if not shared and exp.shape[0] != B:
+            raise ValueError("exp must be [B][ew] or [ew]")
+        if exp_bits is None:
+            exp_bits = 32 * ew
+        if mul_in is not None:
+            mul_in = nat._host_u32(mul_in, (B, k))
+        out = np.empty((B, k), dtype=np.uint32)
+        self._check(self.lib.scb_modexp(self.ctx, slot, nat._ptr(base), nat._ptr(exp), ew, int(shared), int(exp_bits),
+                                        nat._ptr(mul_in), nat._ptr(out), B))
+        return out
+
+    def modmul(self, slot: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        k = self.k32(slot)
+        a = nat._host_u32(a)
+        b = nat._host_u32(b, a.shape)
+        if a.ndim != 2 or a.shape[1] != k:
+            raise ValueError(f"operands must be [B][{k}]")
+        out = np.empty_like(a)
+        self._check(self.lib.scb_modmul(self.ctx, slot, nat._ptr(a), nat._ptr(b), nat._ptr(out), a.shape[0]))
+        return out
+
+    def modinv(self, slot: int, a: np.ndarray, raise_on_failure: bool = True):
+        """Returns ``out`` (and the per-element ``ok`` flags when ``raise_on_failure`` is False)."""
+        k = self.k32(slot)
+        a = nat._host_u32(a)
+        if a.ndim != 2 or a.shape[1] != k:
+            raise ValueError(f"operand must be [B][{k}]")
+        out = np.empty_like(a)
+        ok = np.zeros(a.shape[0], dtype=np.uint8)
+        rc = self.lib.scb_modinv(self.ctx, slot, nat._ptr(a), nat._ptr(out), nat._ptr(ok), a.shape[0])
+        if rc == nat.SCB_ENOTINV and not raise_on_failure:
+            return out, ok
+        self._check(rc)
+        return out if raise_on_failure else (out, ok)
+
+    def fixed_base_load(self, tslot: int, slot: int, base: int, exp_bits: int) -> None:
+        k = self.k32(slot)
+        words = int_to_limbs(base % self.modulus(slot), k)
+        self._check(self.lib.scb_fixed_base_load(self.ctx, tslot, slot, nat._ptr(words), int(exp_bits)))
+        self._fixed_base[tslot] = (slot, exp_bits)
+
+    def fixed_base_exp(self, tslot: int, exp: np.ndarray, mul_in: Optional[np.ndarray] = None) -> np.ndarray:
+        slot, _ = self._fixed_base[tslot]
+        k = self.k32(slot)
+        exp = nat._host_u32(exp)
+        if exp.ndim != 2:
+            raise ValueError("exp must be [B][ew]")
+        B, ew = exp.shape
+        if mul_in is not None:
+            mul_in = nat._host_u32(mul_in, (B, k))
+        out = np.empty((B, k), dtype=np.uint32)
+        self._check(self.lib.scb_fixed_base_exp(self.ctx, tslot, nat._ptr(exp), ew, nat._ptr(mul_in), nat._ptr(out), B))
+        return out
+
+    # ------------------------------------------------------------------ device-buffer primitives
+    def modexp_dev(self, slot: int, base, exp, exp_words: int, exp_shared: bool, exp_bits: int, mul_in, out, B: int) -> None:
+        self._check(self.lib.scb_modexp_dev(self.ctx, slot, nat._ptr(base), nat._ptr(exp), exp_words, int(exp_shared), exp_bits,
+                                            nat._ptr(mul_in), nat._ptr(out), B))
+
+    def modmul_dev(self, slot: int, a, b, out, B: int) -> None:
+        self._check(self.lib.scb_modmul_dev(self.ctx, slot, nat._ptr(a), nat._ptr(b), nat._ptr(out), B))
+
+    def modinv_dev(self, slot: int, a, out, ok, B: int) -> None:
+        self._check(self.lib.scb_modinv_dev(self.ctx, slot, nat._ptr(a), nat._ptr(out), nat._ptr(ok), B))
+
+    def fixed_base_exp_dev(self, tslot: int, exp, exp_words: int, mul_in, out, B: int) -> None:
+        self._check(self.lib.scb_fixed_base_exp_dev(self.ctx, tslot, nat._ptr(exp), exp_words, nat._ptr(mul_in), nat._ptr(out), B))

@@ -1,0 +1,106 @@
+"""GPU parity tests of the generic batched primitives (through the C ABI) against Python integers
+(CPython pow == GMP mpz_powm/mpz_invert results; see tests/test_oracle_golden.py::test_backends_agree)."""
+import random
+
+import numpy as np
+import pytest
+
+from protocols.secure_comparison_b200 import Engine, NotInvertibleError, ints_to_limbs, limbs_to_ints
+from protocols.secure_comparison_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+SLOT = nat.MOD_USER0
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def rand_modulus(rng, bits):
+    return rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+
+
+# (modulus bits, exponent bits, batch) -- every (L, TPI) kernel configuration is covered:
+# K=36 (<=1042 bits), 54, 72, 108, 144, 216, 288
+SIZES = [(64, 64, 40), (128, 160, 70), (1024, 160, 300), (1536, 160, 150), (2048, 400, 300), (2048, 2048, 130),
+         (3072, 400, 100), (4096, 2048, 70), (6144, 64, 40), (8192, 96, 40)]
+
+
+@pytest.mark.parametrize("bits,ebits,B", SIZES)
+def test_modexp_matches_pow(eng, bits, ebits, B):
+    rng = random.Random(bits * 7 + ebits)
+    n = rand_modulus(rng, bits)
+    k = eng.load_modulus(SLOT, n)
+    bases = [rng.randrange(n) for _ in range(B)]
+    exps = [rng.getrandbits(ebits) for _ in range(B)]
+    # edge cases: base 0, 1, n-1; exponent 0, 1, all ones
+    bases[:3] = [0, 1, n - 1]
+    exps[3:6] = [0, 1, (1 << ebits) - 1]
+    ew = (ebits + 31) // 32
+    out = eng.modexp(SLOT, ints_to_limbs(bases, k), ints_to_limbs(exps, ew), ebits)
+    assert limbs_to_ints(out) == [pow(b, e, n) for b, e in zip(bases, exps)]
+    # shared exponent + fused multiplication (the "randomize" shape: c * rho^N)
+    e_shared = rng.getrandbits(ebits) | (1 << (ebits - 1))
+    muls = [rng.randrange(n) for _ in range(B)]
+    out = eng.modexp(SLOT, ints_to_limbs(bases, k), ints_to_limbs([e_shared], ew)[0], ebits, ints_to_limbs(muls, k))
+    assert limbs_to_ints(out) == [m * pow(b, e_shared, n) % n for b, m in zip(bases, muls)]
+
+
+@pytest.mark.parametrize("bits", [64, 1024, 2048, 3072, 4096, 8192])
+def test_modmul_and_edge_moduli(eng, bits):
+    rng = random.Random(bits)
+    for n in (rand_modulus(rng, bits), (1 << bits) - 1, (1 << (bits - 1)) + 1):
+        k = eng.load_modulus(SLOT, n)
+        a = [rng.randrange(n) for _ in range(50)] + [0, n - 1, n - 1, 1]
+        b = [rng.randrange(n) for _ in range(50)] + [5, n - 1, 1, 1]
+        out = eng.modmul(SLOT, ints_to_limbs(a, k), ints_to_limbs(b, k))
+        assert limbs_to_ints(out) == [x * y % n for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("bits", [128, 2048, 4096])
+def test_modinv(eng, bits):
+    rng = random.Random(bits + 1)
+    p, q = rand_modulus(rng, bits // 2), rand_modulus(rng, bits - bits // 2)
+    n = p * q
+    k = eng.load_modulus(SLOT, n)
+    vals = [rng.randrange(1, n) for _ in range(40)] + [1, n - 1, 2]
+    out = eng.modinv(SLOT, ints_to_limbs(vals, k))
+    for v, inv in zip(vals, limbs_to_ints(out)):
+        assert v * inv % n == 1 and inv == pow(v, -1, n)
+    bad = vals[:5] + [0, p, (q * 3) % n]
+    with pytest.raises(NotInvertibleError):
+        eng.modinv(SLOT, ints_to_limbs(bad, k))
+    out, ok = eng.modinv(SLOT, ints_to_limbs(bad, k), raise_on_failure=False)
+    assert ok.tolist() == [1, 1, 1, 1, 1, 0, 0, 0]
+    assert limbs_to_ints(out)[:5] == [pow(v, -1, n) for v in bad[:5]] and limbs_to_ints(out)[5:] == [0, 0, 0]
+
+
+@pytest.mark.parametrize("bits,ebits", [(128, 50), (2048, 400), (3072, 400)])
+def test_fixed_base(eng, bits, ebits):
+    rng = random.Random(bits + ebits)
+    n = rand_modulus(rng, bits)
+    k = eng.load_modulus(SLOT, n)
+    h = rng.randrange(2, n)
+    eng.fixed_base_load(0, SLOT, h, ebits)
+    B = 200
+    exps = [rng.getrandbits(ebits) for _ in range(B)]
+    exps[:3] = [0, 1, (1 << ebits) - 1]
+    muls = [rng.randrange(n) for _ in range(B)]
+    ew = (ebits + 31) // 32
+    out = eng.fixed_base_exp(0, ints_to_limbs(exps, ew))
+    assert limbs_to_ints(out) == [pow(h, e, n) for e in exps]
+    out = eng.fixed_base_exp(0, ints_to_limbs(exps, ew), ints_to_limbs(muls, k))
+    assert limbs_to_ints(out) == [m * pow(h, e, n) % n for e, m in zip(exps, muls)]
+
+
+def test_argument_errors(eng):
+    with pytest.raises(ValueError):
+        eng.load_modulus(SLOT, 1 << 64)           # even modulus
+    k = eng.load_modulus(SLOT, (1 << 127) - 1)
+    with pytest.raises(ValueError):
+        eng.modmul(SLOT, np.zeros((3, k + 1), np.uint32), np.zeros((3, k + 1), np.uint32))
+    assert eng.modmul(SLOT, np.zeros((0, k), np.uint32), np.zeros((0, k), np.uint32)).shape == (0, k)
