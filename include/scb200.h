@@ -103,6 +103,78 @@ int scb_fixed_base_exp(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_wor
 int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
                            uint32_t* out, size_t B);
 
+/* ---- scheme keys ------------------------------------------------------------------------------------
+ * Replace the scheme objects the reference threads through every step (tno.mpc.encryption_schemes
+ * Paillier / DGK: public_key.{n, n_squared, g} / secret_key.{lambda_, mu}; public_key.{n, g, h, u, t} /
+ * secret_key.{v_p, p}).  Key GENERATION stays on the host (keyholder.py:135-172, one-off).            */
+
+/* Paillier public key: N of kN words (g = N + 1 is implied, reference U1).  Loads slots N^2 and N. */
+int scb_paillier_set_public(scb_ctx* ctx, const uint32_t* n, int kN);
+/* Paillier secret key: lambda (any word count) and mu = lambda^-1 mod N (kN words). */
+int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, int lambda_words, const uint32_t* mu);
+/* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1
+ * (unsafe_encrypt(-1, apply_encoding=False), initiator.py:460; pow_mod gives g^-1 mod n); u_bits = bit
+ * length of u (blinding exponents are < u); l = comparison bit length; rand_bits = bit length of the
+ * randomizer exponents rho (h^rho table size).                                                        */
+int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_t* g, const uint32_t* h, const uint32_t* g_neg, int kn,
+                       int u_bits, int l, int rand_bits);
+/* DGK secret key: prime factor p (kp words) and v_p (vp_words words, vp_bits significant bits). */
+int scb_dgk_set_private(scb_ctx* ctx, const uint32_t* p, int kp, const uint32_t* v_p, int vp_words, int vp_bits);
+
+/* ---- Paillier scheme operations ---------------------------------------------------------------------*/
+/* out[i] = (1 + plain[i]*N) * rho[i]^N mod N^2.  plain, rho: [M][kN]; rho nullable = unsafe_encrypt without
+ * randomize().  Replaces Paillier.unsafe_encrypt(m, apply_encoding=False) (+ .randomize()).             */
+int scb_paillier_encrypt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M);
+int scb_paillier_encrypt_dev(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M);
+/* out[i] = L(c[i]^lambda mod N^2) * mu mod N  (raw plaintext in [0, N)).  Replaces
+ * Paillier.decrypt(c, apply_encoding=False): KeyHolder.step_2 (keyholder.py:195) and the final decrypt. */
+int scb_paillier_decrypt(scb_ctx* ctx, const uint32_t* c, uint32_t* out, size_t M);
+int scb_paillier_decrypt_dev(scb_ctx* ctx, const uint32_t* c, uint32_t* out, size_t M);
+/* flags[i] = (c[i]^{v_p} mod p == 1).  Replaces DGK.is_zero (keyholder.py:249). */
+int scb_dgk_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M);
+int scb_dgk_is_zero_dev(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M);
+
+/* ---- fused protocol phases (one call per party-phase of perform_secure_comparison) -------------------
+ * Layouts: Paillier ciphertexts [..][2kN]; Paillier plaintexts / r / Paillier nonces rho [..][kN]; DGK
+ * ciphertexts [..][kn]; per-comparison DGK vectors are [B][l+1][kn] with element 0 = [d] and elements
+ * 1..l = [beta_0]..[beta_{l-1}] (phase B1 -> A2) or [c_0]..[c_l] in the order they are sent (A2 -> B2).
+ * Every nonce array is nullable: NULL skips the corresponding randomize() (the step-by-step flow of
+ * README.md:117-141).                                                                                  */
+
+/* A1: Initiator.step_1 (initiator.py:228-258) + z_enc.randomize() (:109).
+ *     z_enc = y * x^-1 * (1 + (2^l + r) N) * rho^N mod N^2.  r: [B][kN] (the caller draws it: randbelow(N)). */
+int scb_initiator_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32_t* r, const uint32_t* rho, int l,
+                        uint32_t* z_enc, size_t B);
+int scb_initiator_step1_dev(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32_t* r, const uint32_t* rho, int l,
+                            uint32_t* z_enc, size_t B);
+/* B1: KeyHolder.step_4a + step_4b (keyholder.py:198-233) + randomize (:106-108) from the plaintext z of
+ *     step_2 (= scb_paillier_decrypt).  rho: [B][l+1][rho_words] (d first).  db_enc: [B][l+1][kn].       */
+int scb_keyholder_step4ab(scb_ctx* ctx, const uint32_t* z, int l, const uint32_t* rho, int rho_words, uint32_t* db_enc, size_t B);
+int scb_keyholder_step4ab_dev(scb_ctx* ctx, const uint32_t* z, int l, const uint32_t* rho, int rho_words, uint32_t* db_enc, size_t B);
+/* A2: Initiator.step_3, 4c, 4d, 4e, 4f, 4h, 4i (initiator.py:260-516) + randomize (:153-154).
+ *     delta_a: [B] (0/1; s = 1 - 2 delta_a); r_blind: [B][l+1][rb_words] exponents in [1, u-1] in list order
+ *     (NULL = skip the blinding exponentiation, i.e. stop after step_4h); perm: [B][l+1], output position k
+ *     takes the masked value perm[k] (NULL = identity = do_shuffle False); rho: [B][l+1][rho_words] applied in
+ *     OUTPUT order.  c_out: [B][l+1][kn].                                                              */
+int scb_initiator_step4(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const uint8_t* delta_a, const uint32_t* r_blind,
+                        int rb_words, const uint8_t* perm, const uint32_t* rho, int rho_words, int l, uint32_t* c_out, size_t B);
+int scb_initiator_step4_dev(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const uint8_t* delta_a, const uint32_t* r_blind,
+                            int rb_words, const uint8_t* perm, const uint32_t* rho, int rho_words, int l, uint32_t* c_out, size_t B);
+/* B2: KeyHolder.step_4j + step_5 (keyholder.py:235-287) + randomize (:126-128).  rho: [B][3][kN] for
+ *     (zeta_1, zeta_2, delta_B).  delta_b: [B]; enc3: [B][3][2kN] = ([[zeta_1]], [[zeta_2]], [[delta_B]]).     */
+int scb_keyholder_step4j_5(scb_ctx* ctx, const uint32_t* c, const uint32_t* z, const uint32_t* rho, int l, uint8_t* delta_b,
+                           uint32_t* enc3, size_t B);
+int scb_keyholder_step4j_5_dev(scb_ctx* ctx, const uint32_t* c, const uint32_t* z, const uint32_t* rho, int l, uint8_t* delta_b,
+                               uint32_t* enc3, size_t B);
+/*     KeyHolder.step_5 alone (delta_b given). */
+int scb_keyholder_step5(scb_ctx* ctx, const uint32_t* z, const uint8_t* delta_b, const uint32_t* rho, int l, uint32_t* enc3, size_t B);
+int scb_keyholder_step5_dev(scb_ctx* ctx, const uint32_t* z, const uint8_t* delta_b, const uint32_t* rho, int l, uint32_t* enc3, size_t B);
+/* A3: Initiator.step_6 + step_7 (initiator.py:518-564).  result: [B][2kN] = [[x <= y]] (not randomised). */
+int scb_initiator_step6_7(scb_ctx* ctx, const uint32_t* enc3, const uint32_t* r, const uint8_t* delta_a, int l, uint32_t* result,
+                          size_t B);
+int scb_initiator_step6_7_dev(scb_ctx* ctx, const uint32_t* enc3, const uint32_t* r, const uint8_t* delta_a, int l, uint32_t* result,
+                              size_t B);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,28 @@ _SIGNATURES = {
     "scb_fixed_base_load": ([_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int], ctypes.c_int),
     "scb_fixed_base_exp": ([_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_fixed_base_exp_dev": ([_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_paillier_set_public": ([_vp, _vp, ctypes.c_int], ctypes.c_int),
+    "scb_paillier_set_private": ([_vp, _vp, ctypes.c_int, _vp], ctypes.c_int),
+    "scb_dgk_set_public": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int], ctypes.c_int),
+    "scb_dgk_set_private": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
+    "scb_paillier_encrypt": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_paillier_encrypt_dev": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_paillier_decrypt": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_paillier_decrypt_dev": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_dgk_is_zero": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_dgk_is_zero_dev": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step1": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step1_dev": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step4ab": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step4ab_dev": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step4": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step4_dev": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step4j_5": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step4j_5_dev": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step5": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_keyholder_step5_dev": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step6_7": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_initiator_step6_7_dev": ([_vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -217,7 +217,7 @@ __device__ __noinline__ void words_to_digits(const Grp<L, TPI> g, uint32_t* dst,
 // [0, 2^29), then subtract n while >= n (at most `max_sub` times).  Serial in lane 0 of the group;
 // used once per OUTPUT value, never in inner loops.
 template <int L, int TPI>
-__device__ __forceinline__ void canonicalize_staged(const Grp<L, TPI>& g, int max_sub = 2) {
+__device__ __noinline__ void canonicalize_staged(const Grp<L, TPI> g, int max_sub = 2) {
   constexpr int K = Geo<L, TPI>::K;
   constexpr int GPW = Geo<L, TPI>::GPW;
   __syncwarp();
@@ -275,7 +275,7 @@ __device__ __noinline__ void canonical_store(const Grp<L, TPI> g, const uint32_t
 
 // true when the canonical staged value equals the small constant v (all lanes of the group agree)
 template <int L, int TPI>
-__device__ __forceinline__ bool staged_equals_small(const Grp<L, TPI>& g, uint32_t v) {
+__device__ __noinline__ bool staged_equals_small(const Grp<L, TPI> g, uint32_t v) {
   constexpr int GPW = Geo<L, TPI>::GPW;
   bool ok = true;
 #pragma unroll

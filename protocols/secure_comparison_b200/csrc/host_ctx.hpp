@@ -40,6 +40,11 @@ struct scb_ctx {
   std::map<const void*, int> occupancy_cache;
   scb::KeysDev* keys_dev = nullptr;   // protocol-level key material (kernels_protocol.cuh)
   std::vector<uint8_t> keys_host;     // host mirror of KeysDev
+  bool have_paillier_pub = false, have_paillier_priv = false, have_dgk_pub = false, have_dgk_priv = false;
+  std::vector<uint32_t> paillier_lambda, paillier_mu, dgk_vp;
+  int paillier_lambda_bits = 0, dgk_vp_bits = 0, dgk_rand_bits = 0;
+  uint32_t* secret_dev = nullptr;     // lambda words followed by mu words
+  uint32_t* vp_dev = nullptr;         // v_p words
 
   int scratch(int which, size_t bytes, void** out);
   int grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block);
@@ -51,4 +56,6 @@ int fail(scb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what);
 int config_K_for_bits(int bits);
 int modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+// out[i] = a[i*a_stride..] * b[i*b_stride..] mod n (stride 0 broadcasts an operand); device pointers
+int modmul_dev_strided(scb_ctx* ctx, int slot, const uint32_t* a, size_t a_stride, const uint32_t* b, size_t b_stride, uint32_t* out, size_t B);
 }  // namespace scb

@@ -6,6 +6,9 @@ namespace scb {
 
 constexpr int BLOCK_THREADS = 128;
 constexpr int WARPS_PER_BLOCK = BLOCK_THREADS / 32;
+// group kernels: cap registers so that 4 (L = 18) or 3 (L = 27) blocks of 128 threads fit on an SM;
+// mm() itself needs ~110 / ~160 registers, the orchestration code around it may spill a little.
+#define SCB_GROUP_BOUNDS(L) __launch_bounds__(BLOCK_THREADS, ((L) <= 18 ? 4 : 3))
 
 template <int L, int TPI>
 struct GroupIndex {
@@ -69,7 +72,7 @@ __host__ __device__ constexpr size_t modexp_scratch_words(int wbits) {
 
 // out[i] = (mul_in[i] *) base[i]^exp[i] mod n
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp,
          int ewords, size_t exp_stride, int ebits, int wbits, uint32_t* scratch, const uint32_t* __restrict__ mul_in,
          uint32_t* __restrict__ out, int kout, size_t B) {
@@ -102,7 +105,7 @@ k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, in
 
 // out[i] = a[i] * b[i] mod n   (a_stride / b_stride = 0 broadcasts one operand)
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_modmul(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ a, size_t a_stride, const uint32_t* __restrict__ b,
          size_t b_stride, int k32, uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
   extern __shared__ uint32_t smem[];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(32) k_fb_bases(const ModulusDev* __restrict__ 
 
 // step 2 (one group per window j): T[j][0] = 1~, T[j][v] = T[j][v-1] * T[j][1].
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS) k_fb_fill(const ModulusDev* __restrict__ m, uint32_t* table, int nwin, uint32_t* dump) {
+__global__ void SCB_GROUP_BOUNDS(L) k_fb_fill(const ModulusDev* __restrict__ m, uint32_t* table, int nwin, uint32_t* dump) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -184,7 +187,7 @@ __device__ __forceinline__ void group_fixed_base_mul(const Grp<L, TPI>& g, uint3
 }
 
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, const uint32_t* __restrict__ exp, int ewords,
              const uint32_t* __restrict__ mul_in, uint32_t* scratch, uint32_t* __restrict__ out, int k32, size_t B) {
   extern __shared__ uint32_t smem[];
@@ -250,7 +253,7 @@ __device__ __forceinline__ void w_shr1(uint32_t* x, int k, uint32_t top_in) {
   x[k - 1] = (x[k - 1] >> 1) | (top_in << 31);
 }
 
-__global__ void __launch_bounds__(64) k_modinv(const uint32_t* __restrict__ n, int k, const uint32_t* __restrict__ a,
+static __global__ void __launch_bounds__(64) k_modinv(const uint32_t* __restrict__ n, int k, const uint32_t* __restrict__ a,
                                                uint32_t* __restrict__ out, uint8_t* __restrict__ ok, size_t B) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= B) return;

@@ -47,40 +47,27 @@ __device__ __forceinline__ uint64_t mw_low64(const uint32_t* __restrict__ x, int
 }
 __device__ __forceinline__ uint64_t mask_l(int l) { return l >= 64 ? ~0ull : ((1ull << l) - 1ull); }
 
-// out (kout words) = (x (k words) + addend) >> l   with addend in {0, +y (k words)}, plus a small
-// constant `plus` added AFTER the shift.
+// out (kout words) = ((x + y) >> l) + plus   with x, y of k words (y nullable = 0), plus a small constant.
 __device__ __forceinline__ void mw_add_shift(uint32_t* __restrict__ out, int kout, const uint32_t* __restrict__ x,
                                              const uint32_t* __restrict__ y, int k, int l, uint32_t plus) {
-  // sum has k+1 words; produce word j of (sum >> l) on the fly
-  const int ws = l >> 5, bs = l & 31;
+  uint32_t s[MAXW / 2 + 4];
   uint32_t carry = 0;
-  uint32_t prev = 0;                 // sum word (i-1)
-  uint64_t add_carry = plus;
-  for (int i = 0; i <= k + 1; i++) {
-    uint32_t cur;
-    if (i < k) {
-      const uint64_t s = static_cast<uint64_t>(x[i]) + (y ? y[i] : 0u) + carry;
-      cur = static_cast<uint32_t>(s);
-      carry = static_cast<uint32_t>(s >> 32);
-    } else if (i == k) {
-      cur = carry;
-    } else {
-      cur = 0;
-    }
-    // (sum >> l) word j = (sum[j+ws] >> bs) | (sum[j+ws+1] << (32-bs)); emitted when cur = sum[j+ws+1]
-    const int j = i - ws - 1;
-    if (j >= 0 && j < kout) {
-      uint32_t w = bs ? ((prev >> bs) | (cur << (32 - bs))) : prev;
-      const uint64_t t = static_cast<uint64_t>(w) + add_carry;
-      out[j] = static_cast<uint32_t>(t);
-      add_carry = t >> 32;
-    }
-    prev = cur;
+  for (int i = 0; i < k; i++) {
+    const uint64_t t = static_cast<uint64_t>(x[i]) + (y ? y[i] : 0u) + carry;
+    s[i] = static_cast<uint32_t>(t);
+    carry = static_cast<uint32_t>(t >> 32);
   }
-  for (int j = k + 1 - ws; j < kout; j++) {
-    if (j < 0) continue;
-    out[j] = static_cast<uint32_t>(add_carry);
-    add_carry = 0;
+  s[k] = carry;
+  const int ws = l >> 5, bs = l & 31;
+  uint64_t add = plus;
+  for (int j = 0; j < kout; j++) {
+    const int idx = j + ws;
+    const uint32_t lo = idx <= k ? s[idx] : 0u;
+    const uint32_t hi = idx + 1 <= k ? s[idx + 1] : 0u;
+    const uint32_t w = bs ? ((lo >> bs) | (hi << (32 - bs))) : lo;
+    const uint64_t t = static_cast<uint64_t>(w) + add;
+    out[j] = static_cast<uint32_t>(t);
+    add = t >> 32;
   }
 }
 
@@ -89,7 +76,7 @@ __device__ __forceinline__ void mw_add_shift(uint32_t* __restrict__ out, int kou
 // ------------------------------------------------------------------------------------------------
 // Initiator bookkeeping for steps 3, 4c, 4e (initiator.py:260-291, 373):
 //   alpha = r mod 2^l, alpha~ = (r - N) mod 2^l, r_small = (r < (N-1)/2)
-__global__ void k_prep_initiator(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ r, int l, uint64_t* __restrict__ alpha,
+static __global__ void k_prep_initiator(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ r, int l, uint64_t* __restrict__ alpha,
                                  uint64_t* __restrict__ alpha_tilde, uint8_t* __restrict__ r_small, uint8_t* __restrict__ r_bad, size_t B) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= B) return;
@@ -104,7 +91,7 @@ __global__ void k_prep_initiator(const KeysDev* __restrict__ keys, const uint32_
 }
 
 // KeyHolder bookkeeping for steps 2, 4a (keyholder.py:196, 213): beta = z mod 2^l, d = (z < (N-1)/2)
-__global__ void k_prep_keyholder_bits(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ z, int l, uint64_t* __restrict__ beta,
+static __global__ void k_prep_keyholder_bits(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ z, int l, uint64_t* __restrict__ beta,
                                       uint8_t* __restrict__ dflag, size_t B) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= B) return;
@@ -115,7 +102,7 @@ __global__ void k_prep_keyholder_bits(const KeysDev* __restrict__ keys, const ui
 
 // Paillier L function: q = (x - 1) / N exactly (x = 1 mod N), by Hensel division in radix 2^32.
 // x: [B][2kN] words, q: [B][kN] words.
-__global__ void __launch_bounds__(64) k_paillier_L(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ x, uint32_t* __restrict__ q, size_t B) {
+static __global__ void __launch_bounds__(64) k_paillier_L(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ x, uint32_t* __restrict__ q, size_t B) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= B) return;
   const int k = keys->kN;
@@ -148,7 +135,7 @@ __global__ void __launch_bounds__(64) k_paillier_L(const KeysDev* __restrict__ k
 // KeyHolder bookkeeping for steps 4j, 5 (keyholder.py:249-253, 274-287):
 //   delta_b = OR_e flags[e];  m1 = z >> l;  m2 = (z < (N-1)/2) ? (z + N) >> l : m1;  m3 = delta_b
 // plaintext words have kN words each, laid out [B][3][kN].
-__global__ void k_prep_keyholder_step5(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ z, const uint8_t* __restrict__ flags,
+static __global__ void k_prep_keyholder_step5(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ z, const uint8_t* __restrict__ flags,
                                        int nflags, const uint8_t* __restrict__ delta_b_in, int l, uint8_t* __restrict__ delta_b,
                                        uint32_t* __restrict__ plain, size_t B) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -178,7 +165,7 @@ __global__ void k_prep_keyholder_step5(const KeysDev* __restrict__ keys, const u
 //   result = zeta * (1 + e*N) * V   with   e = (N - (r >> l) - (1 - delta_a)) mod N
 //   V = delta_b_enc^-1 (delta_a = 1)  or  delta_b_enc (delta_a = 0)
 // because (1 + aN)^-1 = 1 - aN and (1 - aN)(1 - N) = 1 - (a+1)N  (mod N^2).
-__global__ void k_prep_step67(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ r, const uint8_t* __restrict__ delta_a, int l,
+static __global__ void k_prep_step67(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ r, const uint8_t* __restrict__ delta_a, int l,
                               uint32_t* __restrict__ e, uint8_t* __restrict__ r_small, size_t B) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= B) return;
@@ -203,7 +190,7 @@ __global__ void k_prep_step67(const KeysDev* __restrict__ keys, const uint32_t* 
 // ------------------------------------------------------------------------------------------------
 // pass 1: V[i] = in[i]~ ; P[first] = V[first]; P[i] = P[i-1]*V[i]; Tw[chunk] = canonical(P[last])
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_inv_prefix(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ in, int k32, uint32_t* V, uint32_t* P, uint32_t* tmp_scratch,
              uint32_t* __restrict__ Tw, size_t M, int C) {
   extern __shared__ uint32_t smem[];
@@ -250,7 +237,7 @@ k_inv_prefix(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ in, 
 // pass 2: I = Iw[chunk]~ ; for i = last..first+1: OUT[i] = I*P[i-1]; I = I*V[i]; OUT[first] = I.
 // OUT (Montgomery digits, [M][K]) may alias V.  ok_elem[i] = ok_chunk[chunk].
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_inv_backsub(const ModulusDev* __restrict__ m, const uint32_t* V, const uint32_t* P, const uint32_t* __restrict__ Iw, int k32,
               const uint8_t* __restrict__ ok_chunk, uint32_t* tmp_scratch, uint32_t* OUT, uint8_t* __restrict__ ok_elem, size_t M, int C) {
   extern __shared__ uint32_t smem[];
@@ -287,9 +274,29 @@ k_inv_backsub(const ModulusDev* __restrict__ m, const uint32_t* V, const uint32_
   }
 }
 
+// words -> Montgomery digits (one group per element)
+template <int L, int TPI>
+__global__ void SCB_GROUP_BOUNDS(L)
+k_to_mont(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ in, int k32, uint32_t* tmp_scratch, uint32_t* OUT, size_t M) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  const size_t rounds = (M + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t i = rd * total + slot;
+    const bool active = i < M;
+    uint32_t* dst = active ? OUT + i * K : tmp_scratch + slot * K;
+    if (!active) i = M - 1;
+    words_to_digits(g, dst, in + i * k32, k32);
+    mm<L, TPI>(m, g.sm, dst, dst, m->r2);
+  }
+}
+
 // Montgomery digits -> canonical words (one group per element); used when an ABI call wants words.
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_from_mont(const ModulusDev* __restrict__ m, const uint32_t* D, uint32_t* tmp_scratch, uint32_t* __restrict__ out, int k32,
             const uint8_t* __restrict__ ok, size_t M) {
   extern __shared__ uint32_t smem[];
@@ -357,7 +364,7 @@ __device__ __forceinline__ void group_paillier_encode(const Grp<L, TPI>& g, cons
 // out[i][v] = (1 + plain[i][v] * N) * rho[i][v]^N mod N^2   for v < nv  (keyholder.py:274-287 + 126-128)
 // plain: [B][nv][kN]; rho: [B][nv][kN] or null (no randomisation); out: [B][nv][2kN].
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ plain,
                    const uint32_t* __restrict__ rho, int ebits, int wbits, uint32_t* scratch, uint32_t* __restrict__ out, size_t M) {
   extern __shared__ uint32_t smem[];
@@ -392,7 +399,7 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
 // Initiator.step_1 (+ randomize): z = y * x^-1 * (1 + (2^l + r) N) [* rho^N]  (initiator.py:228-258, 109)
 // xinv: Montgomery digits [B][K] from the batched inversion.
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ y, const uint32_t* xinv,
         const uint32_t* __restrict__ r, const uint32_t* __restrict__ rho, int l, int ebits, int wbits, uint32_t* scratch,
         uint32_t* __restrict__ out, size_t B) {
@@ -438,9 +445,9 @@ k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, cons
 // Fused Initiator.step_6 + step_7 (initiator.py:518-564), see k_prep_step67 for the algebra.
 // dbinv: Montgomery digits of delta_b_enc^-1 ([B][K]).
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_step67(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ zeta1,
-         const uint32_t* __restrict__ zeta2, const uint32_t* __restrict__ delta_b_enc, const uint32_t* dbinv, const uint32_t* __restrict__ e,
+         const uint32_t* __restrict__ zeta2, size_t zstride, const uint32_t* __restrict__ delta_b_enc, const uint32_t* dbinv, const uint32_t* __restrict__ e,
          const uint8_t* __restrict__ r_small, const uint8_t* __restrict__ delta_a, uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
@@ -455,7 +462,7 @@ k_step67(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, con
     size_t i = rd * total + slot;
     const bool active = i < B;
     if (!active) i = B - 1;
-    const uint32_t* zeta = r_small[i] ? zeta1 + i * kc : zeta2 + i * kc;
+    const uint32_t* zeta = r_small[i] ? zeta1 + i * zstride : zeta2 + i * zstride;
     words_to_digits(g, A, zeta, kc);
     mm<L, TPI>(m, g.sm, A, A, m->r2);
     group_paillier_encode(g, keys, T, e + i * kN, kN);
@@ -478,7 +485,7 @@ k_step67(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, con
 // ------------------------------------------------------------------------------------------------
 // element (i, e): e = 0 is d, e = 1..l are beta_0..beta_{l-1}.  rho: [B][l+1][ew] or null.
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_encrypt_bits(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint64_t* __restrict__ beta,
                    const uint8_t* __restrict__ dflag, int l, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew,
                    uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
@@ -519,9 +526,9 @@ __host__ __device__ constexpr size_t step4_scratch_words(int l, int wbits) {
 // pass A: D = r_small ? 1~ : d~ (step 4c), Bm[i] = beta_i~, prefix products P_0 = D, P_{i+1} = P_i * Bm[i];
 // total (canonical words) -> Tw[i].  The prefix products are parked in BI[0..l) (P_1..P_l) and DI (P_0 = D).
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
-k_step4_prefix(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ d_enc,
-               const uint32_t* __restrict__ beta_enc, const uint8_t* __restrict__ r_small, int l, int wbits, uint32_t* scratch,
+__global__ void SCB_GROUP_BOUNDS(L)
+k_step4_prefix(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ db_enc,
+               const uint8_t* __restrict__ r_small, int l, int wbits, uint32_t* scratch,
                uint32_t* __restrict__ Tw, size_t B) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
@@ -547,14 +554,14 @@ k_step4_prefix(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ key
       copy_digits(g, D, m->one);
       mm<L, TPI>(m, g.sm, T, m->one, m->one);                  // dummy: keep the mm count uniform across the warp
     } else {
-      words_to_digits(g, D, d_enc + i * kn, kn);
+      words_to_digits(g, D, db_enc + i * (l + 1) * kn, kn);
       mm<L, TPI>(m, g.sm, D, D, m->r2);
     }
     copy_digits(g, DI, D);
     const uint32_t* prev = DI;
     for (int j = 0; j < l; j++) {
       uint32_t* Bj = Bm + static_cast<size_t>(j) * K;
-      words_to_digits(g, Bj, beta_enc + (i * l + j) * kn, kn);
+      words_to_digits(g, Bj, db_enc + (i * (l + 1) + 1 + j) * kn, kn);
       mm<L, TPI>(m, g.sm, Bj, Bj, m->r2);
       mm<L, TPI>(m, g.sm, BI + static_cast<size_t>(j) * K, prev, Bj);
       prev = BI + static_cast<size_t>(j) * K;
@@ -566,7 +573,7 @@ k_step4_prefix(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ key
 
 // pass B: everything else.  TI: Montgomery digits of the inverse of the total product ([B][K]).
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* TI, const uint64_t* __restrict__ alpha,
              const uint64_t* __restrict__ alpha_tilde, const uint8_t* __restrict__ delta_a, const uint32_t* __restrict__ r_blind, int rb_words,
              const uint8_t* __restrict__ perm, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew, int l,
@@ -656,7 +663,7 @@ k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys,
 // DGK is_zero: flag = (c^{v_p} mod p == 1)   (keyholder.py:249 -> dgk.is_zero)
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+__global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ c, const uint32_t* __restrict__ vp,
               int vp_words, int vp_bits, int wbits, uint32_t* scratch, uint8_t* __restrict__ flags, size_t M) {
   extern __shared__ uint32_t smem[];

@@ -135,6 +135,8 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   for (int i = 0; i < scb_ctx::NSCRATCH; i++)
     if (ctx->scratch_ptr[i]) cudaFree(ctx->scratch_ptr[i]);
   if (ctx->keys_dev) cudaFree(ctx->keys_dev);
+  if (ctx->secret_dev) cudaFree(ctx->secret_dev);
+  if (ctx->vp_dev) cudaFree(ctx->vp_dev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -346,6 +348,13 @@ extern "C" int scb_modmul_dev(scb_ctx* ctx, int slot, const uint32_t* a, const u
   if (!a || !b || !out) return fail(ctx, SCB_EINVAL, "scb_modmul: null pointer");
   const scb_ctx::Mod& md = ctx->mod[slot];
 #define CALL(L, TPI) launch_modmul<L, TPI>(ctx, md, a, md.k32, b, md.k32, out, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
+int scb::modmul_dev_strided(scb_ctx* ctx, int slot, const uint32_t* a, size_t a_stride, const uint32_t* b, size_t b_stride, uint32_t* out, size_t B) {
+  const scb_ctx::Mod& md = ctx->mod[slot];
+#define CALL(L, TPI) launch_modmul<L, TPI>(ctx, md, a, a_stride, b, b_stride, out, B)
   SCB_DISPATCH_K(md.K, CALL)
 #undef CALL
 }

@@ -1,0 +1,298 @@
+"""Batched ``Initiator`` (Alice) -- same step names and argument order as the reference
+(``tno/mpc/protocols/secure_comparison/initiator.py:15-564``), every argument being a batch.
+
+Batch containers: ``[B][k]`` uint32 limb arrays (preferred), or sequences of scheme ciphertext objects /
+ints (converted once at the surface).  Bit vectors are ``[B][l]`` uint8 arrays, LSB first.  Every random
+choice of the reference (``secrets.randbelow`` / ``choice`` at initiator.py:223,250,420,512) can be injected
+through keyword arguments so that the CUDA path can be compared bit for bit with the CPU oracle; when
+left out it is drawn from ``secrets`` exactly like the reference.
+
+The individual ``step_*`` methods mirror the reference one to one and are built from the engine's
+batched primitives; ``steps_4c_to_4i`` and ``steps_6_7`` are the fused single-launch-sequence phases
+the throughput path uses (same results, see tests/test_gpu_protocol.py).
+"""
+from __future__ import annotations
+
+import secrets
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from .communicator import Communicator
+from .limbs import int_to_limbs, ints_to_limbs
+from .schemes import SchemeEngine, as_limbs, get_engine
+from .utils import less_than_const, low_bits, random_below, random_bits, random_permutations, shift_right, to_bits_batch
+
+
+def _bits(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a.reshape(1, -1) if a.ndim == 1 else a
+
+
+def _scheme_of(container, fallback=None):
+    """The reference's ciphertext objects carry their scheme; limb arrays do not (then the scheme given
+    explicitly, or the one already loaded in the engine, is used)."""
+    if fallback is not None:
+        return fallback
+    item = container
+    while isinstance(item, (list, tuple)) and item:
+        item = item[0]
+    return getattr(item, "scheme", None)
+
+
+class Initiator:
+    """Player Alice in the secure comparison protocol, initiates."""
+
+    def __init__(self, l_maximum_bit_length: int, communicator: Optional[Communicator] = None, other_party: str = "",
+                 scheme_paillier: Any = None, scheme_dgk: Any = None, session_id: int = 0) -> None:
+        self.l_maximum_bit_length = l_maximum_bit_length
+        self.communicator = communicator
+        self.other_party = other_party
+        self._scheme_paillier = scheme_paillier
+        self._scheme_dgk = scheme_dgk
+        self.session_id = session_id
+
+    @property
+    def scheme_paillier(self):
+        if self._scheme_paillier is None:
+            raise ValueError("No Paillier scheme has been initialized or received.")
+        return self._scheme_paillier
+
+    @property
+    def scheme_dgk(self):
+        if self._scheme_dgk is None:
+            raise ValueError("No DGK scheme has been initialized or received.")
+        return self._scheme_dgk
+
+    # ------------------------------------------------------------------ driver (initiator.py:69-203)
+    async def perform_secure_comparison(self, x, y, nonces: Optional[dict] = None) -> np.ndarray:
+        """All of Alice's steps for a BATCH of comparisons, with the reference's message ids.
+        ``x`` / ``y``: batches of Paillier ciphertexts (limb arrays or sequences).  Returns ``[B][2kN]``."""
+        if self.communicator is None:
+            raise ValueError("Communicator not properly initialized.")
+        self.session_id += 1
+        session_id = self.session_id
+        await self.receive_encryption_schemes(session_id)
+        l = self.l_maximum_bit_length
+        eng = get_engine(self.scheme_paillier, self.scheme_dgk, l)
+        nonces = nonces or {}
+        x_enc, y_enc = as_limbs(x, eng.kc), as_limbs(y, eng.kc)
+        B = x_enc.shape[0]
+        N = eng.paillier_n
+        r = nonces.get("r")
+        if r is None:
+            r = random_below(N, B, eng.kN)
+        rho_z = nonces.get("rho_z")
+        if rho_z is None:
+            rho_z = random_below(N, B, eng.kN, minimum=1)
+        z_enc = eng.initiator_step1(x_enc, y_enc, r, rho_z, l)                      # step 1 + randomize
+        await self.communicator.send(self.other_party, z_enc, msg_id=f"step_1_session_{session_id}")
+        db_enc = await self.communicator.recv(self.other_party, msg_id=f"step_4b_session_{session_id}")
+        c_is_enc = self.steps_4c_to_4i(db_enc, r, l, self.scheme_dgk, self.scheme_paillier, delta_a=nonces.get("delta_a"),
+                                       r_blind=nonces.get("r_blind"), perm=nonces.get("perm"), rho=nonces.get("rho_c"), randomize=True)
+        await self.communicator.send(self.other_party, c_is_enc, msg_id=f"step_4i_session_{session_id}")
+        enc3 = await self.communicator.recv(self.other_party, msg_id=f"step_5_session_{session_id}")
+        return eng.initiator_step6_7(enc3, r, self._last_delta_a, l)               # steps 6 + 7
+
+    async def receive_encryption_schemes(self, session_id: int = 1) -> None:
+        """Receive the schemes (public parts) from Bob and check them against pre-set ones
+        (initiator.py:177-203, including its ValueErrors)."""
+        if self.communicator is None:
+            raise ValueError("Communicator not properly initialized.")
+        received_paillier, received_dgk = await self.communicator.recv(self.other_party, msg_id=f"schemes_session_{session_id}")
+        if self._scheme_paillier is None:
+            self._scheme_paillier = received_paillier
+        elif self.scheme_paillier != received_paillier:
+            raise ValueError("Readily available Paillier scheme and received Paillier scheme are different.")
+        if self._scheme_dgk is None:
+            self._scheme_dgk = received_dgk
+        elif self.scheme_dgk != received_dgk:
+            raise ValueError("Readily available DGK scheme and received DGK scheme are different.")
+
+    # ------------------------------------------------------------------ steps (static, as in the reference)
+    @staticmethod
+    def step_1(x_enc, y_enc, l: int, scheme_paillier, r: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """``[[z]] = [[y]] * [[x]]^-1 * [[2^l + r]] mod N^2`` (initiator.py:228-258).  Returns ``(z_enc, r)``."""
+        N = int(scheme_paillier.public_key.n)
+        assert (1 << (l + 2)) < N // 2
+        eng = get_engine(scheme_paillier)
+        x, y = as_limbs(x_enc, eng.kc), as_limbs(y_enc, eng.kc)
+        if r is None:
+            r = random_below(N, x.shape[0], eng.kN)
+        r = as_limbs(r, eng.kN)
+        return eng.initiator_step1(x, y, r, None, l), r
+
+    @staticmethod
+    def step_3(r, l: int) -> np.ndarray:
+        """``alpha = r mod 2^l`` as bits (initiator.py:260-270)."""
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        return to_bits_batch(low_bits(r, l), l)
+
+    @staticmethod
+    def step_4c(d_enc, r, scheme_dgk, scheme_paillier) -> np.ndarray:
+        """``[d] <- [0]`` (raw value 1) wherever ``r < (N-1)//2`` (initiator.py:272-291)."""
+        N = int(scheme_paillier.public_key.n)
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        assert bool(np.all(less_than_const(r, N)))          # 0 <= r < N
+        kn = (int(scheme_dgk.public_key.n).bit_length() + 31) // 32
+        d = as_limbs(d_enc, kn).copy()
+        small = less_than_const(r, (N - 1) // 2)
+        d[small] = int_to_limbs(1, kn)
+        return d
+
+    @staticmethod
+    def step_4d(alpha, beta_is_enc, scheme_dgk=None) -> np.ndarray:
+        """``[alpha_i xor beta_i]``: ``[beta_i]`` or ``g * [beta_i]^-1`` (initiator.py:293-328).
+        (The reference finds the scheme on the ciphertext objects; limb arrays need it passed.)"""
+        eng = get_engine(None, _scheme_of(beta_is_enc, scheme_dgk))
+        alpha = _bits(alpha)
+        beta = as_limbs(beta_is_enc, eng.kn)
+        B, l, kn = beta.shape
+        flat = beta.reshape(B * l, kn)
+        inv = eng.modinv(nat.MOD_DGK_N, flat)
+        g = np.broadcast_to(int_to_limbs(eng.dgk_g, kn), flat.shape)
+        flipped = eng.modmul(nat.MOD_DGK_N, inv, np.ascontiguousarray(g))
+        return np.where(alpha.reshape(B * l, 1) != 0, flipped, flat).reshape(B, l, kn)
+
+    @staticmethod
+    def step_4e(r, alpha, alpha_is_xor_beta_is_enc, d_enc, scheme_paillier, scheme_dgk=None) -> Tuple[np.ndarray, np.ndarray]:
+        """``[w_i]`` and ``alpha~ = (r - N) mod 2^l`` (initiator.py:330-384)."""
+        eng = get_engine(None, _scheme_of(alpha_is_xor_beta_is_enc, scheme_dgk))
+        N = int(scheme_paillier.public_key.n)
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        x = as_limbs(alpha_is_xor_beta_is_enc, eng.kn)
+        B, l, kn = x.shape
+        mask = (1 << l) - 1
+        alpha_tilde = to_bits_batch((low_bits(r, 64) - np.uint64(N & 0xFFFFFFFFFFFFFFFF)) & np.uint64(mask), l)
+        alpha = _bits(alpha)
+        d = as_limbs(d_enc, kn)
+        d_inv = eng.modinv(nat.MOD_DGK_N, d)
+        with_d = eng.modmul(nat.MOD_DGK_N, x.reshape(B * l, kn), np.ascontiguousarray(np.repeat(d_inv, l, axis=0)))
+        w = np.where((alpha != alpha_tilde).reshape(B * l, 1), with_d, x.reshape(B * l, kn)).reshape(B, l, kn)
+        return w, alpha_tilde
+
+    @staticmethod
+    def step_4f(w_is_enc, scheme_dgk=None) -> np.ndarray:
+        """``[w_i] <- [w_i]^(2^i) mod n`` (initiator.py:386-410)."""
+        eng = get_engine(None, _scheme_of(w_is_enc, scheme_dgk))
+        w = as_limbs(w_is_enc, eng.kn)
+        B, l, kn = w.shape
+        ew = (l + 31) // 32 + 1
+        exps = np.tile(ints_to_limbs([1 << i for i in range(l)], ew), (B, 1))
+        return eng.modexp(nat.MOD_DGK_N, w.reshape(B * l, kn), exps, exp_bits=l).reshape(B, l, kn)
+
+    @staticmethod
+    def step_4g(batch: int = 1, delta_a: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Uniform bits ``delta_A`` and ``s = 1 - 2 delta_A`` (initiator.py:412-421)."""
+        if delta_a is None:
+            delta_a = np.array([secrets.randbelow(2) for _ in range(batch)], dtype=np.uint8)
+        delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8)
+        return 1 - 2 * delta_a.astype(np.int8), delta_a
+
+    @staticmethod
+    def step_4h(s, alpha, alpha_tilde, d_enc, beta_is_enc, w_is_enc, delta_a, scheme_dgk) -> np.ndarray:
+        """``[c_i]`` with the prepended ``[c_{-1}]`` (initiator.py:423-485); output ``[B][l+1][kn]``.
+        Built from the generic primitives (one batched call per operator of the reference expression)."""
+        eng = get_engine(None, scheme_dgk)
+        M = nat.MOD_DGK_N
+        alpha, alpha_tilde = _bits(alpha), _bits(alpha_tilde)
+        beta = as_limbs(beta_is_enc, eng.kn)
+        w = as_limbs(w_is_enc, eng.kn)
+        B, l, kn = beta.shape
+        d = as_limbs(d_enc, kn)
+        s = np.asarray(s).reshape(B)
+        delta_a = np.asarray(delta_a).reshape(B)
+        pk = scheme_dgk.public_key
+        g = int(pk.g)
+        g_neg = eng.dgk_g_neg
+        one = int_to_limbs(1, kn)
+        mm = lambda a, b: eng.modmul(M, np.ascontiguousarray(a), np.ascontiguousarray(b))  # noqa: E731
+        g_s = np.where((s == 1)[:, None], int_to_limbs(g, kn)[None, :], int_to_limbs(g_neg, kn)[None, :])
+        d_inv = eng.modinv(M, d)
+        beta_inv = eng.modinv(M, beta.reshape(B * l, kn)).reshape(B, l, kn)
+        out = np.empty((B, l + 1, kn), dtype=np.uint32)
+        w_sum = np.tile(one, (B, 1))
+        for i in range(l - 1, -1, -1):
+            v = mm(g_s, np.where((alpha[:, i] != 0)[:, None], int_to_limbs(g, kn)[None, :], one[None, :]))
+            e = alpha_tilde[:, i].astype(np.int8) - alpha[:, i].astype(np.int8)
+            d_pow = np.where((e == 0)[:, None], one[None, :], np.where((e > 0)[:, None], d, d_inv))
+            v = mm(v, d_pow)
+            v = mm(v, beta_inv[:, i])
+            cube = mm(mm(w_sum, w_sum), w_sum)
+            out[:, i + 1] = mm(v, cube)
+            w_sum = mm(w_sum, w[:, i])
+        out[:, 0] = mm(w_sum, np.where((delta_a != 0)[:, None], int_to_limbs(g, kn)[None, :], one[None, :]))
+        return out
+
+    @staticmethod
+    def step_4i(c_is_enc, scheme_dgk, do_shuffle: bool = True, r_blind: Optional[np.ndarray] = None,
+                perm: Optional[np.ndarray] = None) -> np.ndarray:
+        """Blind with ``r_i in [1, u-1]`` and shuffle (initiator.py:487-516)."""
+        eng = get_engine(None, scheme_dgk)
+        c = as_limbs(c_is_enc, eng.kn)
+        B, n_c, kn = c.shape
+        u = int(scheme_dgk.public_key.u)
+        rbw = (u.bit_length() + 31) // 32
+        if r_blind is None:
+            r_blind = random_below(u, B * n_c, rbw, minimum=1).reshape(B, n_c, rbw)
+        r_blind = np.ascontiguousarray(r_blind, dtype=np.uint32).reshape(B * n_c, -1)
+        masked = eng.modexp(nat.MOD_DGK_N, c.reshape(B * n_c, kn), r_blind, exp_bits=u.bit_length()).reshape(B, n_c, kn)
+        if not do_shuffle:
+            return masked
+        if perm is None:
+            perm = random_permutations(B, n_c)
+        perm = np.asarray(perm, dtype=np.int64)
+        return np.take_along_axis(masked, perm[:, :, None], axis=1)
+
+    @staticmethod
+    def step_6(delta_a, delta_b_enc, scheme_paillier=None) -> np.ndarray:
+        """``[[beta < alpha]]``: ``[[delta_B]]`` or ``[[1]] * [[delta_B]]^-1`` (initiator.py:518-531)."""
+        eng = get_engine(scheme_paillier)
+        db = as_limbs(delta_b_enc, eng.kc)
+        delta_a = np.asarray(delta_a).reshape(db.shape[0])
+        inv = eng.modinv(nat.MOD_PAILLIER_N2, db)
+        one_enc = np.tile(int_to_limbs(1 + eng.paillier_n, eng.kc), (db.shape[0], 1))
+        flipped = eng.modmul(nat.MOD_PAILLIER_N2, inv, one_enc)
+        return np.where((delta_a == 1)[:, None], db, flipped)
+
+    @staticmethod
+    def step_7(zeta_1_enc, zeta_2_enc, r, l: int, beta_lt_alpha_enc, scheme_paillier) -> np.ndarray:
+        """``[[x <= y]] = [[zeta]] * ([[r div 2^l]] * [[beta < alpha]])^-1`` (initiator.py:533-564)."""
+        eng = get_engine(scheme_paillier)
+        N = eng.paillier_n
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        z1, z2 = as_limbs(zeta_1_enc, eng.kc), as_limbs(zeta_2_enc, eng.kc)
+        zeta = np.where(less_than_const(r, (N - 1) // 2)[:, None], z1, z2)
+        r_div = eng.paillier_encrypt(shift_right(r, l))
+        t = eng.modmul(nat.MOD_PAILLIER_N2, r_div, as_limbs(beta_lt_alpha_enc, eng.kc))
+        return eng.modmul(nat.MOD_PAILLIER_N2, np.ascontiguousarray(zeta), eng.modinv(nat.MOD_PAILLIER_N2, t))
+
+    # ------------------------------------------------------------------ fused phases
+    def steps_4c_to_4i(self, db_enc, r, l: int, scheme_dgk, scheme_paillier, delta_a=None, r_blind=None, perm=None, rho=None,
+                       randomize: bool = True, do_shuffle: bool = True) -> np.ndarray:
+        """Steps 3, 4c-4i (+ ``randomize()`` of every ``[c_i]``, initiator.py:153-154) in one device pass.
+        ``db_enc``: ``[B][l+1][kn]`` (``[d]`` then ``[beta_i]``) as produced by ``KeyHolder.steps_4a_4b``."""
+        eng = get_engine(scheme_paillier, scheme_dgk, l)
+        db = np.ascontiguousarray(db_enc, dtype=np.uint32)
+        B = db.shape[0]
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        assert bool(np.all(less_than_const(r, eng.paillier_n)))
+        _, delta_a = Initiator.step_4g(B, delta_a)
+        self._last_delta_a = delta_a
+        u = eng.u
+        if r_blind is None:
+            r_blind = random_below(u, B * (l + 1), eng.rb_words, minimum=1).reshape(B, l + 1, eng.rb_words)
+        if perm is None and do_shuffle:
+            perm = random_permutations(B, l + 1)
+        if rho is None and randomize:
+            bits = eng._fixed_base[0][1]
+            rho = random_bits(bits, B * (l + 1), eng.rand_words).reshape(B, l + 1, eng.rand_words)
+        return eng.initiator_step4(db, r, delta_a, r_blind, perm if do_shuffle else None, rho if randomize else None, l)
+
+    @staticmethod
+    def steps_6_7(enc3, r, delta_a, l: int, scheme_paillier) -> np.ndarray:
+        """Steps 6 and 7 fused: ``enc3`` = ``[B][3][2kN]`` (``[[zeta_1]], [[zeta_2]], [[delta_B]]``)."""
+        eng = get_engine(scheme_paillier)
+        return eng.initiator_step6_7(np.ascontiguousarray(enc3, dtype=np.uint32), np.ascontiguousarray(r, dtype=np.uint32),
+                                     np.ascontiguousarray(delta_a, dtype=np.uint8), l)

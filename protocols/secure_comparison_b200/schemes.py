@@ -1,0 +1,250 @@
+"""Scheme-level engine: key loading from (duck-typed) Paillier / DGK scheme objects and the batched
+scheme operations + fused protocol phases of the C ABI.
+
+The scheme objects are consumed through exactly the attribute names the reference uses
+(``paillier.public_key.{n, n_squared, g}``, ``paillier.secret_key.{lambda_, mu}``,
+``dgk.public_key.{n, g, h, u, t}``, ``dgk.secret_key.{v_p, p}``), so real
+``tno.mpc.encryption_schemes`` objects drop in when that package is installed.  Nothing here computes
+a modular exponentiation / inverse / product on the host: the host only derives one-off key constants
+(e.g. the raw ciphertext of plaintext -1) and moves limb arrays.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from .engine import Engine
+from .limbs import int_to_limbs, ints_to_limbs, limbs_for_bits
+
+
+def _raw(ct) -> int:
+    """Raw integer of a ciphertext-like object (scheme ciphertext, or a plain int)."""
+    if isinstance(ct, (int, np.integer)):
+        return int(ct)
+    if hasattr(ct, "peek_value"):
+        return int(ct.peek_value())
+    if hasattr(ct, "get_value"):
+        return int(ct.get_value())
+    raise TypeError(f"cannot read a raw ciphertext value from {type(ct).__name__}")
+
+
+def as_limbs(values, k: int) -> np.ndarray:
+    """Batch container -> ``[..][k]`` uint32 limbs.  Accepts limb arrays (returned as is), a single
+    ciphertext / int (batch of one), or (nested) sequences of ciphertexts / ints."""
+    if isinstance(values, np.ndarray) and values.dtype == np.uint32:
+        if values.shape[-1] != k:
+            raise ValueError(f"limb arrays for this modulus need {k} limbs per value, got {values.shape[-1]}")
+        return np.ascontiguousarray(values)
+    if isinstance(values, (int, np.integer)) or hasattr(values, "peek_value"):
+        return ints_to_limbs([_raw(values)], k)
+    if isinstance(values, np.ndarray):
+        raise TypeError("limb arrays must have dtype uint32")
+    values = list(values)
+    if values and isinstance(values[0], (list, tuple, np.ndarray)):
+        return np.stack([as_limbs(v, k) for v in values])
+    return ints_to_limbs([_raw(v) for v in values], k)
+
+
+def _dgk_raw_of_minus_one(dgk) -> int:
+    """The raw ciphertext the scheme itself produces for plaintext -1 without encoding
+    (``scheme_dgk.unsafe_encrypt(s, apply_encoding=False)`` with s = -1, reference initiator.py:460).
+    Asking the scheme keeps us bit-compatible whatever its negative-exponent convention is."""
+    try:
+        return _raw(dgk.unsafe_encrypt(-1, apply_encoding=False))
+    except Exception:
+        return pow(dgk.public_key.g, -1, dgk.public_key.n)
+
+
+class SchemeEngine(Engine):
+    """One GPU context with a Paillier and a DGK key loaded."""
+
+    def __init__(self, device: int = 0):
+        super().__init__(device)
+        self.paillier_n: Optional[int] = None
+        self.dgk_n: Optional[int] = None
+        self.kN = self.kc = self.kn = 0
+        self.l = 0
+        self.u = 0
+        self.rand_words = 0
+        self.rb_words = 0
+        self.has_paillier_secret = False
+        self.has_dgk_secret = False
+
+    # ------------------------------------------------------------------ keys
+    def load_paillier(self, scheme) -> None:
+        pk = scheme.public_key
+        if getattr(pk, "g", pk.n + 1) != pk.n + 1:
+            raise ValueError("the engine relies on g = n + 1 (reference U1)")
+        n = int(pk.n)
+        if self.paillier_n != n:
+            kN = limbs_for_bits(n.bit_length())
+            self._check(self.lib.scb_paillier_set_public(self.ctx, nat._ptr(int_to_limbs(n, kN)), kN))
+            self.paillier_n, self.kN, self.kc = n, kN, 2 * kN
+            self._moduli[nat.MOD_PAILLIER_N2] = (n * n, 2 * kN)
+            self._moduli[nat.MOD_PAILLIER_N] = (n, kN)
+            self.has_paillier_secret = False
+        sk = getattr(scheme, "secret_key", None)
+        if sk is not None and not self.has_paillier_secret:
+            lam, mu = int(sk.lambda_), int(sk.mu)
+            lw = limbs_for_bits(lam.bit_length())
+            self._check(self.lib.scb_paillier_set_private(self.ctx, nat._ptr(int_to_limbs(lam, lw)), lw, nat._ptr(int_to_limbs(mu, self.kN))))
+            self.has_paillier_secret = True
+
+    def load_dgk(self, scheme, l: int, rand_bits: Optional[int] = None) -> None:
+        pk = scheme.public_key
+        n, u = int(pk.n), int(pk.u)
+        if rand_bits is None:
+            rand_bits = int(getattr(scheme, "randomness_bits", (5 * int(pk.t)) // 2))
+        if self.dgk_n != n or self.l != l or self.rand_words != limbs_for_bits(rand_bits):
+            kn = limbs_for_bits(n.bit_length())
+            g_neg = _dgk_raw_of_minus_one(scheme)
+            self._check(self.lib.scb_dgk_set_public(
+                self.ctx, nat._ptr(int_to_limbs(n, kn)), nat._ptr(int_to_limbs(int(pk.g), kn)), nat._ptr(int_to_limbs(int(pk.h), kn)),
+                nat._ptr(int_to_limbs(g_neg, kn)), kn, u.bit_length(), l, rand_bits))
+            self.dgk_n, self.kn, self.l, self.u = n, kn, l, u
+            self.dgk_g, self.dgk_g_neg = int(pk.g), g_neg
+            self.rand_words = limbs_for_bits(rand_bits)
+            self.rb_words = limbs_for_bits(u.bit_length())
+            self._moduli[nat.MOD_DGK_N] = (n, kn)
+            self._fixed_base[0] = (nat.MOD_DGK_N, rand_bits)
+            self.has_dgk_secret = False
+        sk = getattr(scheme, "secret_key", None)
+        if sk is not None and not self.has_dgk_secret:
+            p, v_p = int(sk.p), int(sk.v_p)
+            kp = limbs_for_bits(p.bit_length())
+            vw = limbs_for_bits(v_p.bit_length())
+            self._check(self.lib.scb_dgk_set_private(self.ctx, nat._ptr(int_to_limbs(p, kp)), kp, nat._ptr(int_to_limbs(v_p, vw)), vw, v_p.bit_length()))
+            self._moduli[nat.MOD_DGK_P] = (p, kp)
+            self.has_dgk_secret = True
+
+    # ------------------------------------------------------------------ scheme operations (host buffers)
+    def paillier_encrypt(self, plain: np.ndarray, rho: Optional[np.ndarray] = None) -> np.ndarray:
+        """``(1 + m N) * rho^N mod N^2`` -- ``unsafe_encrypt(m, apply_encoding=False)`` [+ ``randomize()``]."""
+        plain = nat._host_u32(plain)
+        shape = plain.shape[:-1]
+        M = int(np.prod(shape)) if shape else 1
+        rho_a = None if rho is None else nat._host_u32(rho, plain.shape)
+        out = np.empty(shape + (self.kc,), dtype=np.uint32)
+        self._check(self.lib.scb_paillier_encrypt(self.ctx, nat._ptr(plain), nat._ptr(rho_a), nat._ptr(out), M))
+        return out
+
+    def paillier_decrypt(self, c: np.ndarray) -> np.ndarray:
+        """Raw plaintext in ``[0, N)`` -- ``decrypt(c, apply_encoding=False)``."""
+        c = nat._host_u32(c)
+        shape = c.shape[:-1]
+        M = int(np.prod(shape)) if shape else 1
+        out = np.empty(shape + (self.kN,), dtype=np.uint32)
+        self._check(self.lib.scb_paillier_decrypt(self.ctx, nat._ptr(c), nat._ptr(out), M))
+        return out
+
+    def dgk_is_zero(self, c: np.ndarray) -> np.ndarray:
+        c = nat._host_u32(c)
+        shape = c.shape[:-1]
+        M = int(np.prod(shape)) if shape else 1
+        flags = np.zeros(shape, dtype=np.uint8)
+        self._check(self.lib.scb_dgk_is_zero(self.ctx, nat._ptr(c), nat._ptr(flags), M))
+        return flags
+
+    # ------------------------------------------------------------------ fused phases (host buffers)
+    def initiator_step1(self, x: np.ndarray, y: np.ndarray, r: np.ndarray, rho: Optional[np.ndarray], l: int) -> np.ndarray:
+        x = nat._host_u32(x)
+        B = x.shape[0]
+        y = nat._host_u32(y, (B, self.kc))
+        r = nat._host_u32(r, (B, self.kN))
+        rho_a = None if rho is None else nat._host_u32(rho, (B, self.kN))
+        out = np.empty((B, self.kc), dtype=np.uint32)
+        self._check(self.lib.scb_initiator_step1(self.ctx, nat._ptr(x), nat._ptr(y), nat._ptr(r), nat._ptr(rho_a), l, nat._ptr(out), B))
+        return out
+
+    def keyholder_step4ab(self, z: np.ndarray, l: int, rho: Optional[np.ndarray]) -> np.ndarray:
+        z = nat._host_u32(z)
+        B = z.shape[0]
+        rho_a, rw = None, 0
+        if rho is not None:
+            rho_a = nat._host_u32(rho)
+            if rho_a.shape[:2] != (B, l + 1):
+                raise ValueError("rho must be [B][l+1][words]")
+            rw = rho_a.shape[2]
+        out = np.empty((B, l + 1, self.kn), dtype=np.uint32)
+        self._check(self.lib.scb_keyholder_step4ab(self.ctx, nat._ptr(z), l, nat._ptr(rho_a), rw, nat._ptr(out), B))
+        return out
+
+    def initiator_step4(self, db_enc: np.ndarray, r: np.ndarray, delta_a: np.ndarray, r_blind: Optional[np.ndarray],
+                        perm: Optional[np.ndarray], rho: Optional[np.ndarray], l: int) -> np.ndarray:
+        db_enc = nat._host_u32(db_enc)
+        B = db_enc.shape[0]
+        if db_enc.shape != (B, l + 1, self.kn):
+            raise ValueError(f"db_enc must be [B][{l + 1}][{self.kn}]")
+        r = nat._host_u32(r, (B, self.kN))
+        delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8).reshape(B)
+        rb, rbw = None, 0
+        if r_blind is not None:
+            rb = nat._host_u32(r_blind)
+            if rb.shape[:2] != (B, l + 1):
+                raise ValueError("r_blind must be [B][l+1][words]")
+            rbw = rb.shape[2]
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.uint8).reshape(B, l + 1)
+        rho_a, rw = None, 0
+        if rho is not None:
+            rho_a = nat._host_u32(rho)
+            rw = rho_a.shape[2]
+        out = np.empty((B, l + 1, self.kn), dtype=np.uint32)
+        self._check(self.lib.scb_initiator_step4(self.ctx, nat._ptr(db_enc), nat._ptr(r), nat._ptr(delta_a), nat._ptr(rb), rbw, nat._ptr(pm),
+                                                 nat._ptr(rho_a), rw, l, nat._ptr(out), B))
+        return out
+
+    def keyholder_step4j_5(self, c: np.ndarray, z: np.ndarray, rho: Optional[np.ndarray], l: int) -> Tuple[np.ndarray, np.ndarray]:
+        c = nat._host_u32(c)
+        B = c.shape[0]
+        z = nat._host_u32(z, (B, self.kN))
+        rho_a = None if rho is None else nat._host_u32(rho, (B, 3, self.kN))
+        delta_b = np.zeros(B, dtype=np.uint8)
+        enc3 = np.empty((B, 3, self.kc), dtype=np.uint32)
+        self._check(self.lib.scb_keyholder_step4j_5(self.ctx, nat._ptr(c), nat._ptr(z), nat._ptr(rho_a), l, nat._ptr(delta_b), nat._ptr(enc3), B))
+        return delta_b, enc3
+
+    def keyholder_step5(self, z: np.ndarray, delta_b: np.ndarray, rho: Optional[np.ndarray], l: int) -> np.ndarray:
+        z = nat._host_u32(z)
+        B = z.shape[0]
+        delta_b = np.ascontiguousarray(delta_b, dtype=np.uint8).reshape(B)
+        rho_a = None if rho is None else nat._host_u32(rho, (B, 3, self.kN))
+        enc3 = np.empty((B, 3, self.kc), dtype=np.uint32)
+        self._check(self.lib.scb_keyholder_step5(self.ctx, nat._ptr(z), nat._ptr(delta_b), nat._ptr(rho_a), l, nat._ptr(enc3), B))
+        return enc3
+
+    def initiator_step6_7(self, enc3: np.ndarray, r: np.ndarray, delta_a: np.ndarray, l: int) -> np.ndarray:
+        enc3 = nat._host_u32(enc3)
+        B = enc3.shape[0]
+        r = nat._host_u32(r, (B, self.kN))
+        delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8).reshape(B)
+        out = np.empty((B, self.kc), dtype=np.uint32)
+        self._check(self.lib.scb_initiator_step6_7(self.ctx, nat._ptr(enc3), nat._ptr(r), nat._ptr(delta_a), l, nat._ptr(out), B))
+        return out
+
+
+# -------------------------------------------------------------------------------------------------
+# engine registry: the reference's step functions are static methods that only receive scheme objects,
+# so the batched mirror looks the engine up from the schemes it is given.
+# -------------------------------------------------------------------------------------------------
+_ENGINES: dict = {}
+
+
+def get_engine(scheme_paillier=None, scheme_dgk=None, l: Optional[int] = None, device: int = 0) -> SchemeEngine:
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = _ENGINES[device] = SchemeEngine(device)
+    if scheme_paillier is not None:
+        eng.load_paillier(scheme_paillier)
+    if scheme_dgk is not None:
+        if l is None:
+            l = eng.l or max(1, int(scheme_dgk.public_key.u).bit_length() - 3)
+        eng.load_dgk(scheme_dgk, l)
+    return eng
+
+
+def reset_engines() -> None:
+    for eng in _ENGINES.values():
+        eng.close()
+    _ENGINES.clear()

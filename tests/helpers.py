@@ -32,3 +32,29 @@ def load_golden(name, backend=None, full_decryption=False):
             "non_interactive": Transcript(**unhex(c["non_interactive"])),
         })
     return raw["l"], paillier, dgk, cases
+
+
+# ---------------------------------------------------------------------------------------------
+# packing oracle-side Python ints into the limb arrays of the C ABI
+# ---------------------------------------------------------------------------------------------
+def pack_case_arrays(cases, l, kN, kn, rand_words, rb_words):
+    """cases: list of dicts with x_enc, y_enc (ints) and nonces (oracle.protocol.Nonces)."""
+    import numpy as np
+
+    from protocols.secure_comparison_b200.limbs import ints_to_limbs
+
+    B = len(cases)
+    nc = [c["nonces"] for c in cases]
+    arr = {
+        "x": ints_to_limbs([c["x_enc"] for c in cases], 2 * kN),
+        "y": ints_to_limbs([c["y_enc"] for c in cases], 2 * kN),
+        "r": ints_to_limbs([n.r for n in nc], kN),
+        "rho_z": ints_to_limbs([n.rho_z for n in nc], kN),
+        "delta_a": np.array([n.delta_a for n in nc], dtype=np.uint8),
+        "r_blind": ints_to_limbs([v for n in nc for v in n.r_blind], rb_words).reshape(B, l + 1, rb_words),
+        "perm": np.array([n.perm for n in nc], dtype=np.uint8),
+        "rho_c": ints_to_limbs([v for n in nc for v in n.rho_c], rand_words).reshape(B, l + 1, rand_words),
+        "rho_db": ints_to_limbs([v for n in nc for v in [n.rho_d] + list(n.rho_beta)], rand_words).reshape(B, l + 1, rand_words),
+        "rho_enc3": ints_to_limbs([v for n in nc for v in (n.rho_zeta1, n.rho_zeta2, n.rho_delta_b)], kN).reshape(B, 3, kN),
+    }
+    return arr

@@ -2,7 +2,7 @@
 """Compile the library with -Xptxas -v and print registers / spills per kernel (one line each)."""
 import re, subprocess, sys
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
-       "-Xptxas", "-v", "-o", "protocols/secure_comparison_b200/libscb200.so", "protocols/secure_comparison_b200/csrc/scb200.cu"] + sys.argv[1:]
+       "-Xptxas", "-v", "--threads", "2", "-o", "protocols/secure_comparison_b200/libscb200.so", "protocols/secure_comparison_b200/csrc/scb200.cu", "protocols/secure_comparison_b200/csrc/scb200_protocol.cu"] + sys.argv[1:]
 out = subprocess.run(cmd, capture_output=True, text=True)
 text = out.stderr + out.stdout
 cur = None

@@ -22,15 +22,21 @@ def algorithmic_mac(bits, ebits):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [2048, 4096]
+    args = sys.argv[1:]
+    batches = None
+    if "--batches" in args:
+        j = args.index("--batches")
+        batches = [int(v) for v in args[j + 1].split(",")]
+        args = args[:j] + args[j + 2:]
+    sizes = [int(a) for a in args] or [2048, 4096]
     eng = Engine(0)
     stream = torch.cuda.ExternalStream(eng.stream_ptr)
     rng = random.Random(1)
     for bits in sizes:
         n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
         k = eng.load_modulus(nat.MOD_USER0, n)
-        for B in (1 << 12, 1 << 14, 1 << 16):
-            if bits >= 4096 and B > (1 << 14):
+        for B in (batches or (1 << 12, 1 << 14, 1 << 16)):
+            if batches is None and bits >= 4096 and B > (1 << 14):
                 continue
             base = np.random.default_rng(0).integers(0, 1 << 32, size=(B, k), dtype=np.uint64).astype(np.uint32)
             base[:, -1] &= 0x7FFFFFFF
