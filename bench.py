@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""bench.py -- secure comparisons/s of the batched DGK/Veugen protocol on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                    # our arm (CUDA engine)
+    python bench.py --impl reference --steps 1 --warmup 1            # CPU reference arm (oracle port, GMP)
+    python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...
+
+One "step" = one pass of the whole protocol (all five party-phases: A1 step_1+randomize, B1 decrypt +
+steps 4a/4b+randomize, A2 steps 3,4c-4i+randomize, B2 steps 4j,5+randomize, A3 steps 6,7) over one
+batch of B comparisons with synthetic seeded inputs and host-supplied nonces.  Workload at N=1:
+BASELINE.json configs[1]: B = 65,536, l = 16, Paillier-2048 / DGK-2048 (v = 160).  Multi-GPU: the batch
+shards by comparison index, one process + one context per GPU, no collective on the data path (weak
+scaling: B per GPU is fixed).
+
+`value`  : comparisons/s with every input resident in HBM (device-pointer C-ABI entry points), CUDA
+           events on the engine's stream, max over ranks.
+`e2e`    : the same through the host-buffer C-ABI calls (pinned host buffers; H2D of every input and D2H
+           of every message/result inside the timed region).
+`roofline`: integer-multiply pipe (IMAD.WIDE.U32), not HBM / tensor: see DESIGN.md section "Roofline".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "secure comparisons/sec (Paillier-2048/DGK-2048, l=16)"
+UNIT = "comparisons/s"
+# measured on this pool's B200 (profiles/r01_imad_microbench2.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM
+INT_PEAK_MAC_PER_S = 148 * 32 * 1.965e9
+MAC_PER_COMPARISON_L16 = 567e6      # SURVEY.md section 8d, reference-faithful op list, 32x32->64 MAC
+MAC_PER_MODEXP_4096_2048 = 81.91e6  # one rho^N mod N^2 (k = 128 limbs, 2048-bit exponent)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="comparisons per GPU per step")
+    ap.add_argument("--l", type=int, default=16)
+    ap.add_argument("--cpu-per-core", type=int, default=6, help="comparisons per host core in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- workload
+def make_workload(B: int, l: int, seed: int, eng, paillier):
+    """Seeded synthetic batch: plaintext pairs, nonces (host numpy), input ciphertexts made on the GPU (untimed)."""
+    import numpy as np
+
+    from oracle.workload import REFERENCE_PAIRS   # fixed (x, y) pairs of the reference's tests; data only
+
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
+    y = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
+    fixed = [(a, b) for a, b in REFERENCE_PAIRS if a >= 0] + [(23, 42), (42, 23), (7, 7), (0, 0), ((1 << l) - 1, (1 << l) - 1)]
+    for i, (a, b) in enumerate(fixed[:B]):
+        x[i], y[i] = a, b
+    kN, kn = eng.kN, eng.kn
+
+    def rand_limbs(shape, top_mask=0x7FFFFFFF):
+        a = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64).astype(np.uint32)
+        a[..., -1] &= top_mask          # < 2^(32k-1) <= N: N has its top bit set
+        return a
+
+    def rand_bits(shape_words, bits):
+        a = rng.integers(0, 1 << 32, size=shape_words, dtype=np.uint64).astype(np.uint32)
+        extra = 32 * shape_words[-1] - bits
+        if extra:
+            a[..., -1] &= (1 << (32 - extra)) - 1
+        return a
+
+    rand_bits_n = eng._fixed_base[0][1]
+    u = eng.u
+    r_blind = np.zeros((B, l + 1, eng.rb_words), dtype=np.uint32)
+    r_blind[..., 0] = rng.integers(1, min(u, 1 << 32), size=(B, l + 1), dtype=np.uint64).astype(np.uint32)   # in [1, u-1] (u < 2^32 for l <= 29)
+    perm = np.argsort(rng.random((B, l + 1)), axis=1).astype(np.uint8)
+    plain = np.zeros((2, B, kN), dtype=np.uint32)
+    plain[0, :, 0] = (x & 0xFFFFFFFF).astype(np.uint32)
+    plain[1, :, 0] = (y & 0xFFFFFFFF).astype(np.uint32)
+    if kN > 1:
+        plain[0, :, 1] = (x >> 32).astype(np.uint32)
+        plain[1, :, 1] = (y >> 32).astype(np.uint32)
+    rho_in = rand_limbs((2, B, kN))
+    rho_in[..., 0] |= 1
+    enc = eng.paillier_encrypt(plain.reshape(2 * B, kN), rho_in.reshape(2 * B, kN)).reshape(2, B, 2 * kN)
+    w = {
+        "x": enc[0], "y": enc[1], "r": rand_limbs((B, kN)), "rho_z": rand_limbs((B, kN)) | np.uint32(0),
+        "delta_a": rng.integers(0, 2, size=B, dtype=np.uint8), "r_blind": r_blind, "perm": perm,
+        "rho_c": rand_bits((B, l + 1, eng.rand_words), rand_bits_n), "rho_db": rand_bits((B, l + 1, eng.rand_words), rand_bits_n),
+        "rho_enc3": rand_limbs((B, 3, kN)),
+    }
+    w["rho_z"][:, 0] |= 1
+    w["rho_enc3"][..., 0] |= 1
+    truth = (x <= y).astype(np.uint8)
+    return w, truth
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from oracle.workload import make_schemes     # seeded key cache (tests/golden/keys_*.json); keys are data
+    from protocols.secure_comparison_b200 import SchemeEngine
+    from protocols.secure_comparison_b200 import _native as nat
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, l = args.batch, args.l
+    paillier, dgk = make_schemes(2048, 2048, 160, l)
+    eng = SchemeEngine(local)
+    eng.load_paillier(paillier)
+    eng.load_dgk(dgk, l)
+    w, truth = make_workload(B, l, seed=1234 + rank, eng=eng, paillier=paillier)
+    kN, kc, kn = eng.kN, eng.kc, eng.kn
+    stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    lib, ctx = eng.lib, eng.ctx
+
+    def dev(a):
+        t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+        return t
+
+    d = {k: dev(v) for k, v in w.items()}
+    i32 = dict(dtype=torch.int32, device="cuda")
+    d_z_enc = torch.empty((B, kc), **i32)
+    d_z = torch.empty((B, kN), **i32)
+    d_db = torch.empty((B, l + 1, kn), **i32)
+    d_c = torch.empty((B, l + 1, kn), **i32)
+    d_delta_b = torch.empty((B,), dtype=torch.uint8, device="cuda")
+    d_enc3 = torch.empty((B, 3, kc), **i32)
+    d_res = torch.empty((B, kc), **i32)
+    d_bit = torch.empty((B, kN), **i32)
+    p = nat._ptr
+
+    def step_device():
+        eng._check(lib.scb_initiator_step1_dev(ctx, p(d["x"]), p(d["y"]), p(d["r"]), p(d["rho_z"]), l, p(d_z_enc), B))
+        eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_z_enc), p(d_z), B))
+        eng._check(lib.scb_keyholder_step4ab_dev(ctx, p(d_z), l, p(d["rho_db"]), eng.rand_words, p(d_db), B))
+        eng._check(lib.scb_initiator_step4_dev(ctx, p(d_db), p(d["r"]), p(d["delta_a"]), p(d["r_blind"]), eng.rb_words, p(d["perm"]),
+                                               p(d["rho_c"]), eng.rand_words, l, p(d_c), B))
+        eng._check(lib.scb_keyholder_step4j_5_dev(ctx, p(d_c), p(d_z), p(d["rho_enc3"]), l, p(d_delta_b), p(d_enc3), B))
+        eng._check(lib.scb_initiator_step6_7_dev(ctx, p(d_enc3), p(d["r"]), p(d["delta_a"]), l, p(d_res), B))
+
+    def barrier():
+        torch.cuda.synchronize()
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also grows every scratch buffer to its final size)
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    eng.sync()
+    launches_before = eng.launch_count
+
+    # ---- timed region, device resident
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.steps):
+                step_device()
+            e1.record(stream)
+        eng.sync()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches_before
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- parity gate on the last step's output: decrypted bits == plaintext truth for 100 % of the batch
+    eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_res), p(d_bit), B))
+    eng.sync()
+    bits = d_bit.cpu().numpy().view(np.uint32)
+    bits_ok = bool(np.array_equal(bits[:, 0].astype(np.uint8), truth) and not bits[:, 1:].any())
+
+    # ---- per-kernel timing of one more step (events after every launch) for the roofline of the dominant kernel
+    eng.profile_begin()
+    step_device()
+    kernels = eng.profile_end()
+    step_ms_prof = sum(k["ms"] for k in kernels.values())
+    top_name = max(kernels, key=lambda k: kernels[k]["ms"])
+    enc = kernels.get("k_paillier_encrypt", {"ms": 0.0, "launches": 1})
+    enc_ms = enc["ms"] / max(enc["launches"], 1)
+    enc_mac = 3 * B * MAC_PER_MODEXP_4096_2048          # 3B randomizers rho^N mod N^2 per launch (+ the 1 + mN encodings, negligible)
+    achieved = enc_mac / (enc_ms * 1e-3) / 1e12 if enc_ms else 0.0
+    bytes_per_launch = 3 * B * (2 * kN * 4 + 2 * kc * 4)   # plaintext + rho in, ciphertext out (algorithmic HBM bytes)
+    roofline = {
+        "bound": "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy; not hbm, not tensor)",
+        "kernel": "k_paillier_encrypt", "kernel_share_of_step": round(enc["ms"] / step_ms_prof, 4) if step_ms_prof else None,
+        "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic)",
+        "frac": round(achieved * 1e12 / INT_PEAK_MAC_PER_S, 4),
+        "peak_source": "measured: profiles/r01_imad_microbench2.jsonl (IMAD.WIDE.U32 = 32 lanes/clk/SM x 148 SMs x 1.965 GHz)",
+        "traffic": None,
+        "hbm_gbs_algorithmic": round(bytes_per_launch / (enc_ms * 1e-3) / 1e9, 2) if enc_ms else None,
+        "whole_step_frac": round(value / world * MAC_PER_COMPARISON_L16 / INT_PEAK_MAC_PER_S, 4),
+        "top_kernel_by_time": top_name,
+        "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+
+    # ---- e2e: host buffers through the synchronous C-ABI calls (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        h = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory().numpy() for k, v in w.items()}
+        h = {k: (v.view(np.uint32) if v.dtype == np.int32 else v) for k, v in h.items()}
+
+        def step_host():
+            z_enc = eng.initiator_step1(h["x"], h["y"], h["r"], h["rho_z"], l)
+            z = eng.paillier_decrypt(z_enc)
+            db = eng.keyholder_step4ab(z, l, h["rho_db"])
+            c = eng.initiator_step4(db, h["r"], h["delta_a"], h["r_blind"], h["perm"], h["rho_c"], l)
+            delta_b, enc3 = eng.keyholder_step4j_5(c, z, h["rho_enc3"], l)
+            return eng.initiator_step6_7(enc3, h["r"], h["delta_a"], l)
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_host()
+        eng.sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        E = (l + 1) * kn * 4
+        h2d = B * (2 * kc * 4 + 2 * kN * 4) + B * kc * 4 + B * (kN * 4 + (l + 1) * eng.rand_words * 4) + \
+            B * (E + kN * 4 + 1 + (l + 1) * (eng.rb_words * 4 + 1 + eng.rand_words * 4)) + B * (E + kN * 4 + 3 * kN * 4) + B * (3 * kc * 4 + kN * 4 + 1)
+        d2h = B * kc * 4 + B * kN * 4 + B * E + B * E + B * (1 + 3 * kc * 4) + B * kc * 4
+        same = bool(np.array_equal(res, d_res.cpu().numpy().view(np.uint32)))
+        e2e = {"value": round(world * B * args.steps / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import time_comparisons
+        cpu = time_comparisons(2048, 2048, 160, l, per_core=args.cpu_per_core)
+        cpu = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in cpu.items()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (29-bit digits, 64-bit accumulators)",
+            "data": "synthetic (seeded keys, inputs and host-supplied nonces)",
+            "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-2048/DGK-2048 (v=160), interactive flow (all randomize() calls)",
+                       "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l},
+            "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "modexp_4096_per_s_in_encrypt_kernel": round(3 * B / (enc_ms * 1e-3), 1) if enc_ms else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if not bits_ok:
+        raise SystemExit("bench.py: parity gate failed (decrypted bits differ from the plaintext truth)")
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU path (oracle port over GMP: the reference + gmpy2 cannot be installed offline),
+    all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import time_comparisons
+    vals = []
+    for i in range(args.warmup if args.warmup < 2 else 1):
+        time_comparisons(2048, 2048, 160, args.l, per_core=1)
+    res = None
+    for _ in range(args.steps):
+        res = time_comparisons(2048, 2048, 160, args.l, per_core=args.cpu_per_core)
+        vals.append(res["value"])
+    value = sum(vals) / len(vals)
+    done_per_step = args.cpu_per_core * res["cores"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(done_per_step / value * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "arbitrary-precision int (GMP mpz)",
+        "data": "synthetic (seeded keys, inputs and nonces)",
+        "config": {"workload": f"bounded sample of the batch-of-{args.batch} workload: {done_per_step} comparisons per step, l={args.l}, "
+                               "Paillier-2048/DGK-2048 (v=160), interactive flow", "l": args.l},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

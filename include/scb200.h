@@ -62,6 +62,11 @@ void* scb_stream(scb_ctx* ctx);                   /* the context's cudaStream_t 
 int scb_version(void);
 /* number of kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 unsigned long long scb_launch_count(const scb_ctx* ctx);
+/* Per-kernel device timing.  Between scb_profile_begin and scb_profile_end one CUDA event is recorded on the
+ * context's stream after every kernel launch; _end synchronises and writes a JSON object
+ * {"kernel": {"ms": total, "launches": n}, ...} (time of a kernel = gap to the previous event). */
+int scb_profile_begin(scb_ctx* ctx);
+int scb_profile_end(scb_ctx* ctx, char* json_out, size_t json_bytes);
 /* pinned host memory for callers that want DMA-able staging buffers */
 int scb_host_alloc(size_t bytes, void** out);
 int scb_host_free(void* ptr);

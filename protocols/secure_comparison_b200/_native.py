@@ -31,6 +31,8 @@ _SIGNATURES = {
     "scb_stream": ([_vp], _vp),
     "scb_version": ([], ctypes.c_int),
     "scb_launch_count": ([_vp], ctypes.c_ulonglong),
+    "scb_profile_begin": ([_vp], ctypes.c_int),
+    "scb_profile_end": ([_vp, ctypes.c_char_p, ctypes.c_size_t], ctypes.c_int),
     "scb_host_alloc": ([ctypes.c_size_t, ctypes.POINTER(_vp)], ctypes.c_int),
     "scb_host_free": ([_vp], ctypes.c_int),
     "scb_modulus_load": ([_vp, ctypes.c_int, _vp, ctypes.c_int], ctypes.c_int),

@@ -46,6 +46,10 @@ struct scb_ctx {
   uint32_t* secret_dev = nullptr;     // lambda words followed by mu words
   uint32_t* vp_dev = nullptr;         // v_p words
 
+  // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the previous event
+  bool profiling = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
+
   int scratch(int which, size_t bytes, void** out);
   int grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block);
   int launched(const char* what);

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -314,6 +315,55 @@ int scb_ctx::launched(const char* what) {
   launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(this, e, what);
+  if (profiling) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) == cudaSuccess) {
+      cudaEventRecord(ev, stream);
+      prof_events.push_back({what, ev});
+    }
+  }
+  return SCB_OK;
+}
+
+extern "C" int scb_profile_begin(scb_ctx* ctx) {
+  if (!ctx) return SCB_EINVAL;
+  cudaSetDevice(ctx->device);
+  for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.second);
+  ctx->prof_events.clear();
+  ctx->profiling = true;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return SCB_ECUDA;
+  cudaEventRecord(ev, ctx->stream);
+  ctx->prof_events.push_back({"<begin>", ev});
+  return SCB_OK;
+}
+
+extern "C" int scb_profile_end(scb_ctx* ctx, char* out, size_t out_bytes) {
+  if (!ctx || !out || out_bytes < 2) return SCB_EINVAL;
+  ctx->profiling = false;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
+  std::map<std::string, std::pair<double, int>> acc;   // name -> (ms, launches)
+  for (size_t i = 1; i < ctx->prof_events.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->prof_events[i - 1].second, ctx->prof_events[i].second);
+    auto& a = acc[ctx->prof_events[i].first];
+    a.first += ms;
+    a.second += 1;
+  }
+  for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.second);
+  ctx->prof_events.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : acc) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.4f, \"launches\": %d}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  if (js.size() + 1 > out_bytes) return fail(ctx, SCB_EINVAL, "scb_profile_end: buffer too small");
+  memcpy(out, js.c_str(), js.size() + 1);
   return SCB_OK;
 }
 

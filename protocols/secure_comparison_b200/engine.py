@@ -73,6 +73,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.scb_launch_count(self.ctx))
 
+    def profile_begin(self) -> None:
+        self._check(self.lib.scb_profile_begin(self.ctx))
+
+    def profile_end(self) -> dict:
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._check(self.lib.scb_profile_end(self.ctx, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     # ------------------------------------------------------------------ moduli
     def load_modulus(self, slot: int, modulus: int, k32: Optional[int] = None) -> int:
         """Load an odd modulus; returns the limb count ``k32`` every operand of this slot must have."""

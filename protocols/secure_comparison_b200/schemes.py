@@ -80,7 +80,8 @@ class SchemeEngine(Engine):
         n = int(pk.n)
         if self.paillier_n != n:
             kN = limbs_for_bits(n.bit_length())
-            self._check(self.lib.scb_paillier_set_public(self.ctx, nat._ptr(int_to_limbs(n, kN)), kN))
+            n_w = int_to_limbs(n, kN)                      # keep the arrays alive across the C call
+            self._check(self.lib.scb_paillier_set_public(self.ctx, nat._ptr(n_w), kN))
             self.paillier_n, self.kN, self.kc = n, kN, 2 * kN
             self._moduli[nat.MOD_PAILLIER_N2] = (n * n, 2 * kN)
             self._moduli[nat.MOD_PAILLIER_N] = (n, kN)
@@ -89,7 +90,8 @@ class SchemeEngine(Engine):
         if sk is not None and not self.has_paillier_secret:
             lam, mu = int(sk.lambda_), int(sk.mu)
             lw = limbs_for_bits(lam.bit_length())
-            self._check(self.lib.scb_paillier_set_private(self.ctx, nat._ptr(int_to_limbs(lam, lw)), lw, nat._ptr(int_to_limbs(mu, self.kN))))
+            lam_w, mu_w = int_to_limbs(lam, lw), int_to_limbs(mu, self.kN)
+            self._check(self.lib.scb_paillier_set_private(self.ctx, nat._ptr(lam_w), lw, nat._ptr(mu_w)))
             self.has_paillier_secret = True
 
     def load_dgk(self, scheme, l: int, rand_bits: Optional[int] = None) -> None:
@@ -100,9 +102,9 @@ class SchemeEngine(Engine):
         if self.dgk_n != n or self.l != l or self.rand_words != limbs_for_bits(rand_bits):
             kn = limbs_for_bits(n.bit_length())
             g_neg = _dgk_raw_of_minus_one(scheme)
-            self._check(self.lib.scb_dgk_set_public(
-                self.ctx, nat._ptr(int_to_limbs(n, kn)), nat._ptr(int_to_limbs(int(pk.g), kn)), nat._ptr(int_to_limbs(int(pk.h), kn)),
-                nat._ptr(int_to_limbs(g_neg, kn)), kn, u.bit_length(), l, rand_bits))
+            n_w, g_w, h_w, gn_w = (int_to_limbs(v, kn) for v in (n, int(pk.g), int(pk.h), g_neg))
+            self._check(self.lib.scb_dgk_set_public(self.ctx, nat._ptr(n_w), nat._ptr(g_w), nat._ptr(h_w), nat._ptr(gn_w), kn,
+                                                    u.bit_length(), l, rand_bits))
             self.dgk_n, self.kn, self.l, self.u = n, kn, l, u
             self.dgk_g, self.dgk_g_neg = int(pk.g), g_neg
             self.rand_words = limbs_for_bits(rand_bits)
@@ -115,7 +117,8 @@ class SchemeEngine(Engine):
             p, v_p = int(sk.p), int(sk.v_p)
             kp = limbs_for_bits(p.bit_length())
             vw = limbs_for_bits(v_p.bit_length())
-            self._check(self.lib.scb_dgk_set_private(self.ctx, nat._ptr(int_to_limbs(p, kp)), kp, nat._ptr(int_to_limbs(v_p, vw)), vw, v_p.bit_length()))
+            p_w, vp_w = int_to_limbs(p, kp), int_to_limbs(v_p, vw)
+            self._check(self.lib.scb_dgk_set_private(self.ctx, nat._ptr(p_w), kp, nat._ptr(vp_w), vw, v_p.bit_length()))
             self._moduli[nat.MOD_DGK_P] = (p, kp)
             self.has_dgk_secret = True
 

@@ -1,0 +1,154 @@
+"""GPU parity tests of the scheme-level operations (Paillier encrypt / randomize / decrypt, DGK bit
+encryption / is_zero, the phase building blocks) against Python integers, one operation at a time."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.protocol import Oracle
+from oracle.workload import make_schemes
+from protocols.secure_comparison_b200 import get_engine, ints_to_limbs, limbs_to_ints, reset_engines
+from protocols.secure_comparison_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+KEYS = [(1024, 128, 20, 16), (512, 192, 24, 8), (2048, 2048, 160, 16)]
+
+
+@pytest.fixture(scope="module", params=KEYS, ids=lambda k: f"p{k[0]}d{k[1]}l{k[3]}")
+def setup(request):
+    pb, db, vb, l = request.param
+    paillier, dgk = make_schemes(pb, db, vb, l)
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    return paillier, dgk, l, eng, Oracle(paillier, dgk, "auto"), random.Random(pb + l)
+
+
+def test_paillier_encrypt_and_randomize(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    B = 37
+    m = [rng.randrange(N) for _ in range(B)]
+    m[:4] = [0, 1, N - 1, 2 ** l]
+    rho = [rng.randrange(1, N) for _ in range(B)]
+    out = eng.paillier_encrypt(ints_to_limbs(m, eng.kN))
+    assert limbs_to_ints(out) == [(1 + v * N) % N2 for v in m]
+    out = eng.paillier_encrypt(ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN))
+    assert limbs_to_ints(out) == [(1 + v * N) * pow(r, N, N2) % N2 for v, r in zip(m, rho)]
+
+
+def test_paillier_decrypt(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    m = [rng.randrange(N) for _ in range(20)] + [0, 1, N - 1]
+    c = [(1 + v * N) * pow(rng.randrange(1, N), N, N2) % N2 for v in m]
+    c += [1, N2 - 2, rng.randrange(1, N2)]          # arbitrary group elements decrypt like the oracle says
+    want = [oracle.paillier_decrypt_raw(v) for v in c]
+    assert want[:len(m)] == m
+    assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want
+
+
+def test_step1_pieces(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    B = 45                                           # > one inversion chunk, ragged second chunk
+    x = [rng.randrange(1, N2) for _ in range(B)]
+    y = [rng.randrange(1, N2) for _ in range(B)]
+    r = [rng.randrange(N) for _ in range(B)]
+    r[:3] = [0, N - 1, (N - 1) // 2]
+    rho = [rng.randrange(1, N) for _ in range(B)]
+    X, Y, R, RHO = (ints_to_limbs(v, k) for v, k in ((x, eng.kc), (y, eng.kc), (r, eng.kN), (rho, eng.kN)))
+    got = limbs_to_ints(eng.initiator_step1(X, Y, R, None, l))
+    want = [oracle.step_1(a, b, l, c) for a, b, c in zip(x, y, r)]
+    bad = [i for i in range(B) if got[i] != want[i]]
+    assert not bad, f"step_1 without randomize differs at {bad[:10]}"
+    got = limbs_to_ints(eng.initiator_step1(X, Y, R, RHO, l))
+    want = [oracle.paillier_randomize(oracle.step_1(a, b, l, c), d) for a, b, c, d in zip(x, y, r, rho)]
+    bad = [i for i in range(B) if got[i] != want[i]]
+    assert not bad, f"step_1 + randomize differs at {bad[:10]}"
+
+
+def test_dgk_bit_encryption(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N = paillier.public_key.n
+    B = 23
+    z = [rng.randrange(N) for _ in range(B)]
+    z[:3] = [0, (N - 1) // 2, (N - 1) // 2 - 1]
+    bits = dgk.randomness_bits
+    rho = [[rng.getrandbits(bits) for _ in range(l + 1)] for _ in range(B)]
+    out = eng.keyholder_step4ab(ints_to_limbs(z, eng.kN), l, None)
+    want = [[oracle.step_4a(v, l)] + oracle.step_4b(v % (1 << l), l) for v in z]
+    assert limbs_to_ints(out.reshape(B * (l + 1), -1)) == [c for row in want for c in row]
+    RHO = ints_to_limbs([e for row in rho for e in row], eng.rand_words).reshape(B, l + 1, eng.rand_words)
+    out = eng.keyholder_step4ab(ints_to_limbs(z, eng.kN), l, RHO)
+    want_r = [oracle.dgk_randomize(c, e) for row, erow in zip(want, rho) for c, e in zip(row, erow)]
+    assert limbs_to_ints(out.reshape(B * (l + 1), -1)) == want_r
+
+
+def test_dgk_is_zero(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    n, u = dgk.public_key.n, dgk.public_key.u
+    ms = [0, 1, u - 1, 0, 5, 0] + [rng.randrange(u) for _ in range(30)]
+    c = [pow(dgk.public_key.g, m, n) * pow(dgk.public_key.h, rng.getrandbits(dgk.randomness_bits), n) % n for m in ms]
+    c += [1, n - 1, rng.randrange(1, n)]
+    flags = eng.dgk_is_zero(ints_to_limbs(c, eng.kn))
+    assert flags.tolist() == [int(oracle.dgk_is_zero(v)) for v in c]
+    assert flags[:6].tolist() == [1, 0, 0, 1, 0, 1]
+
+
+def test_step5_and_step67(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    B = 40
+    z = [rng.randrange(N) for _ in range(B)]
+    z[:4] = [0, 100, (N - 1) // 2, N - 1]
+    db = [rng.randrange(2) for _ in range(B)]
+    rho = [[rng.randrange(1, N) for _ in range(3)] for _ in range(B)]
+    r = [rng.randrange(N) for _ in range(B)]
+    r[:4] = [0, N - 1, (1 << l) - 1, (N - 1) // 2]
+    da = [rng.randrange(2) for _ in range(B)]
+    enc3 = eng.keyholder_step5(ints_to_limbs(z, eng.kN), np.array(db, dtype=np.uint8), None, l)
+    want = [oracle.step_5(a, l, b) for a, b in zip(z, db)]
+    assert limbs_to_ints(enc3.reshape(3 * B, -1)) == [v for t in want for v in t]
+    RHO = ints_to_limbs([e for row in rho for e in row], eng.kN).reshape(B, 3, eng.kN)
+    enc3r = eng.keyholder_step5(ints_to_limbs(z, eng.kN), np.array(db, dtype=np.uint8), RHO, l)
+    want_r = [[oracle.paillier_randomize(c, e) for c, e in zip(t, er)] for t, er in zip(want, rho)]
+    assert limbs_to_ints(enc3r.reshape(3 * B, -1)) == [v for t in want_r for v in t]
+    res = eng.initiator_step6_7(enc3r, ints_to_limbs(r, eng.kN), np.array(da, dtype=np.uint8), l)
+    want_res = [oracle.step_7(t[0], t[1], rr, l, oracle.step_6(a, t[2])) for t, rr, a in zip(want_r, r, da)]
+    bad = [i for i in range(B) if limbs_to_ints(res)[i] != want_res[i]]
+    assert not bad, f"steps 6+7 differ at {bad[:10]} (delta_a {[da[i] for i in bad[:10]]})"
+
+
+def test_step4_without_blinding_and_with(setup):
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, n, u = paillier.public_key.n, dgk.public_key.n, dgk.public_key.u
+    B = 19
+    cases = []
+    for i in range(B):
+        z = rng.randrange(N)
+        r = rng.randrange(N) if i % 3 else rng.randrange((N - 1) // 2)
+        d = oracle.dgk_randomize(oracle.step_4a(z, l), rng.getrandbits(64))
+        beta = [oracle.dgk_randomize(b, rng.getrandbits(64)) for b in oracle.step_4b(z % (1 << l), l)]
+        cases.append((r, d, beta, rng.randrange(2)))
+    DB = ints_to_limbs([v for r, d, beta, da in cases for v in [d] + beta], eng.kn).reshape(B, l + 1, eng.kn)
+    R = ints_to_limbs([c[0] for c in cases], eng.kN)
+    DA = np.array([c[3] for c in cases], dtype=np.uint8)
+
+    def oracle_4h(r, d, beta, da):
+        alpha = oracle.step_3(r, l)
+        d4c = oracle.step_4c(d, r)
+        xor = oracle.step_4d(alpha, beta)
+        w, at = oracle.step_4e(r, alpha, xor, d4c)
+        w = oracle.step_4f(w)
+        return oracle.step_4h(1 - 2 * da, alpha, at, d4c, beta, w, da)
+
+    want = [oracle_4h(*c) for c in cases]
+    got = eng.initiator_step4(DB, R, DA, None, None, None, l)
+    assert limbs_to_ints(got.reshape(B * (l + 1), -1)) == [v for row in want for v in row], "steps 4c-4h"
+    rb = [[rng.randrange(1, u) for _ in range(l + 1)] for _ in range(B)]
+    perm = [rng.sample(range(l + 1), l + 1) for _ in range(B)]
+    RB = ints_to_limbs([v for row in rb for v in row], eng.rb_words).reshape(B, l + 1, eng.rb_words)
+    got = eng.initiator_step4(DB, R, DA, RB, np.array(perm, dtype=np.uint8), None, l)
+    want_i = [oracle.step_4i(row, e, p) for row, e, p in zip(want, rb, perm)]
+    assert limbs_to_ints(got.reshape(B * (l + 1), -1)) == [v for row in want_i for v in row], "step 4i"
