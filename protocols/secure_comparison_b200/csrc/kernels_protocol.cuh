@@ -199,7 +199,11 @@ k_inv_prefix(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ in, 
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
   const size_t slot = GI::slot(), total = GI::total();
   const size_t nchunks = (M + C - 1) / C;
-  uint32_t* TMP = tmp_scratch + slot * K;
+  // two private slots per group: TMP (products of surplus / padded positions) and TMPV (their operands).
+  // Every group executes the SAME sequence of mm() calls (mm shuffles across the whole warp), so padded
+  // positions of a ragged chunk and surplus groups run the arithmetic on private dummies.
+  uint32_t* TMP = tmp_scratch + slot * 2 * K;
+  uint32_t* TMPV = TMP + K;
   const size_t rounds = (nchunks + total - 1) / total;
   for (size_t rd = 0; rd < rounds; rd++) {
     size_t chunk = rd * total + slot;
@@ -210,25 +214,23 @@ k_inv_prefix(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ in, 
       size_t i = first + j;
       const bool valid = i < M;             // ragged last chunk: pad with the identity
       if (!valid) i = M - 1;
-      uint32_t* Vi = active ? V + i * K : TMP;
-      uint32_t* Pi = active ? P + i * K : TMP;
-      if (valid) {
-        words_to_digits(g, Vi, in + i * k32, k32);
-        mm<L, TPI>(m, g.sm, Vi, Vi, m->r2);
-      }
+      const bool real = active && valid;
+      uint32_t* Vi = real ? V + i * K : TMPV;
+      uint32_t* Pi = real ? P + i * K : TMP;
+      words_to_digits(g, Vi, in + i * k32, k32);
+      mm<L, TPI>(m, g.sm, Vi, Vi, m->r2);
       const uint32_t* Vsrc = valid ? Vi : m->one;
       if (j == 0) {
-        if (active && valid) copy_digits(g, Pi, Vi);
-        // (keep the warp converged: a dummy product for the other lanes' benefit is not needed, mm is only
-        //  called below for j > 0 and every group reaches it the same number of times)
+        copy_digits(g, Pi, Vi);              // j == 0 is always a valid position
       } else {
-        const uint32_t* Pprev = active ? P + (first + j - 1 < M ? first + j - 1 : M - 1) * K : TMP;
-        mm<L, TPI>(m, g.sm, (valid ? Pi : TMP), Pprev, Vsrc);
-        if (!valid && active) copy_digits(g, TMP, TMP);
+        // previous prefix: the real one for active groups (also across padded positions, where it is
+        // carried forward unchanged in TMP), the private slot for surplus groups
+        const uint32_t* Pprev = !active ? TMP : (first + j - 1 < M ? P + (first + j - 1) * K : TMP);
+        mm<L, TPI>(m, g.sm, Pi, Pprev, Vsrc);
       }
     }
     const size_t last = (first + C - 1 < M) ? first + C - 1 : M - 1;
-    const uint32_t* Plast = active ? P + last * K : TMP;
+    const uint32_t* Plast = (active && first + C - 1 < M) ? P + last * K : TMP;
     mm<L, TPI>(m, g.sm, TMP, Plast, m->unit);
     canonical_store(g, TMP, Tw + chunk * k32, k32, active);
   }
@@ -468,12 +470,11 @@ k_step67(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, con
     group_paillier_encode(g, keys, T, e + i * kN, kN);
     mm<L, TPI>(m, g.sm, A, A, T);
     // V: delta_a = 1 -> dbinv (Montgomery); delta_a = 0 -> delta_b_enc (ordinary words: a*R * v / R = a*v, then still *R)
-    if (delta_a[i]) {
-      copy_digits(g, T, dbinv + i * K);
-    } else {
-      words_to_digits(g, T, delta_b_enc + i * kc, kc);
-      mm<L, TPI>(m, g.sm, T, T, m->r2);
-    }
+    // (both variants are formed by every group: mm() shuffles across the whole warp, so it must never sit
+    //  in a branch that depends on per-comparison data)
+    words_to_digits(g, T, delta_b_enc + i * kc, kc);
+    mm<L, TPI>(m, g.sm, T, T, m->r2);
+    if (delta_a[i]) copy_digits(g, T, dbinv + i * K);
     mm<L, TPI>(m, g.sm, A, A, T);
     mm<L, TPI>(m, g.sm, A, A, m->unit);
     canonical_store(g, A, out + i * kc, kc, active);
@@ -550,13 +551,9 @@ k_step4_prefix(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ key
     uint32_t* T = D + 4 * K;
     uint32_t* Bm = D + 6 * K;
     uint32_t* BI = Bm + static_cast<size_t>(l) * K;
-    if (r_small[i]) {
-      copy_digits(g, D, m->one);
-      mm<L, TPI>(m, g.sm, T, m->one, m->one);                  // dummy: keep the mm count uniform across the warp
-    } else {
-      words_to_digits(g, D, db_enc + i * (l + 1) * kn, kn);
-      mm<L, TPI>(m, g.sm, D, D, m->r2);
-    }
+    words_to_digits(g, D, db_enc + i * (l + 1) * kn, kn);
+    mm<L, TPI>(m, g.sm, D, D, m->r2);                          // uniform across the warp (mm shuffles warp-wide)
+    if (r_small[i]) copy_digits(g, D, m->one);                 // step 4c: [d] <- [0] = 1
     copy_digits(g, DI, D);
     const uint32_t* prev = DI;
     for (int j = 0; j < l; j++) {
