@@ -36,6 +36,7 @@ constexpr int W = 29;
 constexpr uint32_t DMASK = (1u << W) - 1u;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int MAXK = 288;   // digits of the largest supported modulus (8192-bit N^2 of Paillier-4096)
+constexpr int INV_MAXL = 280;   // signed 30-bit limbs of the widest operand of the modular-inverse kernel
 
 // Montgomery constants of one modulus (global memory; written once by scb_modulus_load).
 struct ModulusDev {
@@ -48,6 +49,11 @@ struct ModulusDev {
   uint32_t r2[MAXK];    // R^2 mod n    (x -> x*R)
   uint32_t r3[MAXK];    // R^3 mod n
   uint32_t unit[MAXK];  // the integer 1 (x*R -> x)
+  // modular-inverse kernel (k_modinv): n as 30-bit limbs, n^-1 mod 2^30, limb count, outer-iteration cap
+  int len30;
+  int inv_cap;
+  uint32_t ninv30;
+  int32_t n30[INV_MAXL];
 };
 
 template <int L, int TPI>

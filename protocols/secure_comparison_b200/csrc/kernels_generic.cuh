@@ -214,81 +214,167 @@ k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, 
 }
 
 // -------------------------------------------------------------------------------------------------
-// Modular inverse, one thread per element, binary extended Euclid on 32-bit words in local memory.
-// Invariants: x1*a = u, x2*a = v (mod n); v stays odd.  Not on the throughput-critical path: the
-// protocol kernels batch their inversions with Montgomery's trick so this runs once per ~64 values.
+// Modular inverse, one thread per element: Bernstein-Yang "safegcd" divsteps in batches of 30 (the
+// transition-matrix formulation; data flow pinned by tests/safegcd_model.py).  Big numbers are signed
+// 30-bit limbs in thread-local memory; one outer iteration = 30 branch-free divsteps on the low limbs,
+// then two matrix-vector updates over the limbs ((f, g) exactly divided by 2^30, (d, e) mod n).
+// ~2.05 divsteps per modulus bit, i.e. ~10 * len * (bits / 14.6) multiply-adds per inverse: microseconds
+// of work where a bit-serial binary Euclid needs seconds.  Not on the throughput-critical path anyway:
+// the protocol kernels batch their inversions with Montgomery's trick (one inverse per 32 values).
 // -------------------------------------------------------------------------------------------------
-constexpr int INV_MAXW = 260;
+constexpr int INV_MAXW = 260;     // 32-bit words of the widest operand
+constexpr uint32_t M30 = (1u << 30) - 1u;
 
-__device__ __forceinline__ bool w_is_zero(const uint32_t* x, int k) {
-  for (int i = 0; i < k; i++)
-    if (x[i]) return false;
-  return true;
-}
-__device__ __forceinline__ bool w_less(const uint32_t* x, const uint32_t* y, int k) {
-  for (int i = k - 1; i >= 0; i--)
-    if (x[i] != y[i]) return x[i] < y[i];
-  return false;
-}
-__device__ __forceinline__ uint32_t w_sub(uint32_t* x, const uint32_t* y, int k) {   // x -= y, returns borrow
-  uint32_t borrow = 0;
-  for (int i = 0; i < k; i++) {
-    const uint64_t d = static_cast<uint64_t>(x[i]) - y[i] - borrow;
-    x[i] = static_cast<uint32_t>(d);
-    borrow = static_cast<uint32_t>(d >> 63);
+struct Trans30 {
+  int32_t u, v, q, r;
+};
+
+// 30 divsteps on the low bits of f, g; zeta = -(delta + 1/2).  t * (f, g) = 2^30 * (f', g').
+__device__ __forceinline__ int32_t divsteps_30(int32_t zeta, uint32_t f, uint32_t g, Trans30& t) {
+  uint32_t u = 1, v = 0, q = 0, r = 1;
+#pragma unroll 6
+  for (int i = 0; i < 30; i++) {
+    uint32_t c1 = static_cast<uint32_t>(zeta >> 31);
+    const uint32_t c2 = 0u - (g & 1u);
+    const uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+    g += x & c2;
+    q += y & c2;
+    r += z & c2;
+    c1 &= c2;
+    zeta = (zeta ^ static_cast<int32_t>(c1)) - 1;
+    f += g & c1;
+    u += q & c1;
+    v += r & c1;
+    g >>= 1;
+    u <<= 1;
+    v <<= 1;
   }
-  return borrow;
-}
-__device__ __forceinline__ uint32_t w_add(uint32_t* x, const uint32_t* y, int k) {   // x += y, returns carry
-  uint32_t carry = 0;
-  for (int i = 0; i < k; i++) {
-    const uint64_t s = static_cast<uint64_t>(x[i]) + y[i] + carry;
-    x[i] = static_cast<uint32_t>(s);
-    carry = static_cast<uint32_t>(s >> 32);
-  }
-  return carry;
-}
-__device__ __forceinline__ void w_shr1(uint32_t* x, int k, uint32_t top_in) {
-  for (int i = 0; i < k - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
-  x[k - 1] = (x[k - 1] >> 1) | (top_in << 31);
+  t.u = static_cast<int32_t>(u);
+  t.v = static_cast<int32_t>(v);
+  t.q = static_cast<int32_t>(q);
+  t.r = static_cast<int32_t>(r);
+  return zeta;
 }
 
-static __global__ void __launch_bounds__(64) k_modinv(const uint32_t* __restrict__ n, int k, const uint32_t* __restrict__ a,
-                                               uint32_t* __restrict__ out, uint8_t* __restrict__ ok, size_t B) {
+__device__ __forceinline__ void words_to_limbs30(int32_t* dst, int len, const uint32_t* __restrict__ w, int k) {
+  uint64_t acc = 0;
+  int have = 0, wi = 0;
+  for (int i = 0; i < len; i++) {
+    if (have < 30 && wi < k) {
+      acc |= static_cast<uint64_t>(w[wi++]) << have;
+      have += 32;
+    }
+    dst[i] = static_cast<int32_t>(static_cast<uint32_t>(acc) & M30);
+    acc >>= 30;
+    have = have >= 30 ? have - 30 : 0;
+  }
+}
+
+static __global__ void __launch_bounds__(64) k_modinv(const ModulusDev* __restrict__ m, int k, const uint32_t* __restrict__ a,
+                                                      uint32_t* __restrict__ out, uint8_t* __restrict__ ok, size_t B) {
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= B) return;
-  uint32_t bufU[INV_MAXW], bufV[INV_MAXW], bufX1[INV_MAXW], bufX2[INV_MAXW];
-  uint32_t *u = bufU, *v = bufV, *x1 = bufX1, *x2 = bufX2;
-  for (int i = 0; i < k; i++) {
-    u[i] = a[idx * k + i];
-    v[i] = n[i];
-    x1[i] = 0;
-    x2[i] = 0;
+  int32_t f[INV_MAXL], g[INV_MAXL], d[INV_MAXL], e[INV_MAXL];
+  const int len = m->len30;
+  const int32_t* __restrict__ mod = m->n30;
+  const uint32_t ninv30 = m->ninv30;
+  words_to_limbs30(g, len, a + idx * k, k);
+  for (int i = 0; i < len; i++) {
+    f[i] = mod[i];
+    d[i] = 0;
+    e[i] = 0;
   }
-  x1[0] = 1;
-  // reduce a below n if needed (inputs are residues, but stay safe): a >= n -> a -= n while possible
-  for (int guard = 0; guard < 4 && !w_less(u, v, k); guard++) w_sub(u, v, k);
-  while (!w_is_zero(u, k)) {
-    while ((u[0] & 1u) == 0) {
-      w_shr1(u, k, 0);
-      if (x1[0] & 1u) {
-        const uint32_t carry = w_add(x1, n, k);
-        w_shr1(x1, k, carry);
-      } else {
-        w_shr1(x1, k, 0);
+  e[0] = 1;
+  int32_t zeta = -1;
+  bool done = false;
+  const int cap = m->inv_cap;
+  for (int it = 0; it < cap && !done; it++) {
+    Trans30 t;
+    zeta = divsteps_30(zeta, static_cast<uint32_t>(f[0]) | (static_cast<uint32_t>(f[1]) << 30),
+                       static_cast<uint32_t>(g[0]) | (static_cast<uint32_t>(g[1]) << 30), t);
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    // (d, e) <- t * (d, e) / 2^30 mod n, kept in (-2n, n)
+    {
+      const int32_t sd = d[len - 1] >> 31, se = e[len - 1] >> 31;
+      int32_t md = (t.u & sd) + (t.v & se), me = (t.q & sd) + (t.r & se);
+      int64_t cd = u * d[0] + v * e[0], ce = q * d[0] + r * e[0];
+      md -= static_cast<int32_t>((ninv30 * static_cast<uint32_t>(cd) + static_cast<uint32_t>(md)) & M30);
+      me -= static_cast<int32_t>((ninv30 * static_cast<uint32_t>(ce) + static_cast<uint32_t>(me)) & M30);
+      cd += static_cast<int64_t>(mod[0]) * md;
+      ce += static_cast<int64_t>(mod[0]) * me;
+      cd >>= 30;
+      ce >>= 30;
+      for (int i = 1; i < len; i++) {
+        const int64_t di = d[i], ei = e[i], mi = mod[i];
+        cd += u * di + v * ei + mi * md;
+        ce += q * di + r * ei + mi * me;
+        d[i - 1] = static_cast<int32_t>(static_cast<uint32_t>(cd) & M30);
+        e[i - 1] = static_cast<int32_t>(static_cast<uint32_t>(ce) & M30);
+        cd >>= 30;
+        ce >>= 30;
       }
+      d[len - 1] = static_cast<int32_t>(cd);
+      e[len - 1] = static_cast<int32_t>(ce);
     }
-    if (w_less(u, v, k)) {
-      uint32_t* t = u; u = v; v = t;
-      t = x1; x1 = x2; x2 = t;
+    // (f, g) <- t * (f, g) / 2^30 (exact)
+    {
+      int64_t cf = u * f[0] + v * g[0], cg = q * f[0] + r * g[0];
+      cf >>= 30;
+      cg >>= 30;
+      uint32_t any = 0;
+      for (int i = 1; i < len; i++) {
+        const int64_t fi = f[i], gi = g[i];
+        cf += u * fi + v * gi;
+        cg += q * fi + r * gi;
+        f[i - 1] = static_cast<int32_t>(static_cast<uint32_t>(cf) & M30);
+        const uint32_t gl = static_cast<uint32_t>(cg) & M30;
+        g[i - 1] = static_cast<int32_t>(gl);
+        any |= gl;
+        cf >>= 30;
+        cg >>= 30;
+      }
+      f[len - 1] = static_cast<int32_t>(cf);
+      g[len - 1] = static_cast<int32_t>(cg);
+      any |= static_cast<uint32_t>(cg);
+      done = any == 0;
     }
-    w_sub(u, v, k);
-    if (w_sub(x1, x2, k)) w_add(x1, n, k);       // x1 = (x1 - x2) mod n
   }
-  bool one = v[0] == 1;
-  for (int i = 1; i < k && one; i++) one = v[i] == 0;
-  for (int i = 0; i < k; i++) out[idx * k + i] = one ? x2[i] : 0u;
-  ok[idx] = one ? 1 : 0;
+  // f = +-gcd(a, n): the inverse exists iff f = +-1
+  const bool fneg = f[len - 1] < 0;
+  bool unit = done;
+  if (fneg) {
+    for (int i = 0; i < len - 1 && unit; i++) unit = static_cast<uint32_t>(f[i]) == M30;
+    unit = unit && f[len - 1] == -1;
+  } else {
+    unit = unit && f[0] == 1;
+    for (int i = 1; i < len && unit; i++) unit = f[i] == 0;
+  }
+  // d * sign(f) mod n into [0, n)
+  for (int pass = 0; pass < 2; pass++) {
+    const int32_t add = d[len - 1] >> 31;
+    const int32_t neg = (pass == 0 && fneg) ? -1 : 0;
+    for (int i = 0; i < len; i++) {
+      int32_t x = d[i] + (mod[i] & add);
+      d[i] = (x ^ neg) - neg;
+    }
+    for (int i = 0; i < len - 1; i++) {
+      d[i + 1] += d[i] >> 30;
+      d[i] &= static_cast<int32_t>(M30);
+    }
+  }
+  // limbs -> words
+  uint64_t acc = 0;
+  int have = 0, li = 0;
+  for (int w = 0; w < k; w++) {
+    while (have < 32 && li < len) {
+      acc |= static_cast<uint64_t>(static_cast<uint32_t>(d[li++])) << have;
+      have += 30;
+    }
+    out[idx * k + w] = unit ? static_cast<uint32_t>(acc) : 0u;
+    acc >>= 32;
+    have -= 32;
+  }
+  ok[idx] = unit ? 1 : 0;
 }
 
 }  // namespace scb

@@ -163,7 +163,7 @@ extern "C" int scb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSucces
 // modulus constants
 // -------------------------------------------------------------------------------------------------
 extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k32) {
-  if (!ctx || !n || slot < 0 || slot >= SCB_MOD_SLOTS || k32 <= 0 || k32 > INV_MAXW - 2) return fail(ctx, SCB_EINVAL, "scb_modulus_load: bad argument");
+  if (!ctx || !n || slot < 0 || slot >= SCB_MOD_SLOTS || k32 <= 0 || k32 > INV_MAXW - 2 || (32 * k32 + 2 + 29) / 30 > INV_MAXL) return fail(ctx, SCB_EINVAL, "scb_modulus_load: bad argument");
   if ((n[0] & 1u) == 0) return fail(ctx, SCB_EINVAL, "scb_modulus_load: modulus must be odd");
   Words nn(n, n + k32);
   const int bits = words_bits(nn);
@@ -193,6 +193,16 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
   for (int t = 0; t < 3; t++) {
     for (; e < targets[t]; e++) words_dbl_mod(x, nw);
     words_to_digits(x, dst[t], K);
+  }
+  // safegcd constants of k_modinv: n in 30-bit limbs, n^-1 mod 2^30; operands are k32-word values
+  h.len30 = (32 * k32 + 2 + 29) / 30;
+  h.inv_cap = (49 * 32 * k32 + 57) / 17 / 30 + 2;
+  h.ninv30 = inv & ((1u << 30) - 1u);
+  for (int i = 0; i < h.len30; i++) {
+    const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+    uint64_t v = (w < k32) ? n[w] : 0u;
+    if (w + 1 < k32) v |= static_cast<uint64_t>(n[w + 1]) << 32;
+    h.n30[i] = static_cast<int32_t>(static_cast<uint32_t>(v >> sh) & ((1u << 30) - 1u));
   }
   scb_ctx::Mod& md = ctx->mod[slot];
   if (!md.dev) {
@@ -411,12 +421,7 @@ int scb::modmul_dev_strided(scb_ctx* ctx, int slot, const uint32_t* a, size_t a_
 
 int scb::modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B) {
   const scb_ctx::Mod& md = ctx->mod[slot];
-  void* nwords = nullptr;
-  int rc = ctx->scratch(1, sizeof(uint32_t) * md.k32, &nwords);
-  if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(nwords, md.words.data(), sizeof(uint32_t) * md.k32, cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "upload modulus words");
-  k_modinv<<<static_cast<unsigned>((B + 63) / 64), 64, 0, ctx->stream>>>(static_cast<const uint32_t*>(nwords), md.k32, a, out, ok, B);
+  k_modinv<<<static_cast<unsigned>((B + 63) / 64), 64, 0, ctx->stream>>>(md.dev, md.k32, a, out, ok, B);
   return ctx->launched("k_modinv");
 }
 

@@ -154,26 +154,23 @@ int batch_modinv_mont(scb_ctx* ctx, int slot, const uint32_t* in, size_t M, uint
   Arena vp, sm;
   int rc = get_arena(ctx, SC_INV_VP, pad256(sizeof(uint32_t) * M * C::K), &vp);
   if (rc) return rc;
-  rc = get_arena(ctx, SC_INV_SMALL, 2 * pad256(sizeof(uint32_t) * G * k32) + pad256(G) + pad256(sizeof(uint32_t) * groups * 2 * C::K) + pad256(sizeof(uint32_t) * k32), &sm);
+  rc = get_arena(ctx, SC_INV_SMALL, 2 * pad256(sizeof(uint32_t) * G * k32) + pad256(G) + pad256(sizeof(uint32_t) * groups * 2 * C::K), &sm);
   if (rc) return rc;
   uint32_t* P = vp.take<uint32_t>(M * C::K);
   uint32_t* Tw = sm.take<uint32_t>(G * k32);
   uint32_t* Iw = sm.take<uint32_t>(G * k32);
   uint8_t* okc = sm.take<uint8_t>(G);
   uint32_t* tmp = sm.take<uint32_t>(groups * 2 * C::K);
-  uint32_t* nwords = sm.take<uint32_t>(k32);
-  cudaError_t e = cudaMemcpyAsync(nwords, md.words.data(), sizeof(uint32_t) * k32, cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "upload modulus words");
   uint32_t* V = OUT;   // the Montgomery forms of the inputs live in the output buffer until back-substitution replaces them
   k_inv_prefix<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, in, k32, V, P, tmp, Tw, M, chunk);
   if ((rc = ctx->launched("k_inv_prefix"))) return rc;
-  k_modinv<<<static_cast<unsigned>((G + 63) / 64), 64, 0, ctx->stream>>>(nwords, k32, Tw, Iw, okc, G);
+  k_modinv<<<static_cast<unsigned>((G + 63) / 64), 64, 0, ctx->stream>>>(md.dev, k32, Tw, Iw, okc, G);
   if ((rc = ctx->launched("k_modinv"))) return rc;
   k_inv_backsub<L, TPI><<<grid2, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, V, P, Iw, k32, okc, tmp, OUT, ok_elem, M, chunk);
   if ((rc = ctx->launched("k_inv_backsub"))) return rc;
   // did any chunk fail?  (G bytes back to the host)
   std::vector<uint8_t> hok(G);
-  e = cudaMemcpyAsync(hok.data(), okc, G, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaMemcpyAsync(hok.data(), okc, G, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "download inversion flags");
   bool failed = false;
@@ -186,7 +183,7 @@ int batch_modinv_mont(scb_ctx* ctx, int slot, const uint32_t* in, size_t M, uint
   if (rc) return rc;
   uint32_t* invw = slow.take<uint32_t>(M * k32);
   uint32_t* tmp2 = slow.take<uint32_t>(groups * C::K);
-  k_modinv<<<static_cast<unsigned>((M + 63) / 64), 64, 0, ctx->stream>>>(nwords, k32, in, invw, ok_elem, M);
+  k_modinv<<<static_cast<unsigned>((M + 63) / 64), 64, 0, ctx->stream>>>(md.dev, k32, in, invw, ok_elem, M);
   if ((rc = ctx->launched("k_modinv"))) return rc;
   const int grid3 = ctx->grid_for(reinterpret_cast<const void*>(&k_to_mont<L, TPI>), C::SMEM, M, C::GPB);
   k_to_mont<L, TPI><<<std::min(grid3, std::max(grid, grid2)), BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, invw, k32, tmp2, OUT, M);
