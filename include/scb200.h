@@ -117,6 +117,14 @@ int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp
 int scb_paillier_set_public(scb_ctx* ctx, const uint32_t* n, int kN);
 /* Paillier secret key: lambda (any word count) and mu = lambda^-1 mod N (kN words). */
 int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, int lambda_words, const uint32_t* mu);
+/* Paillier secret key in CRT form: the primes p, q (kN/2 words each, p*q = N).  The KeyHolder's Paillier work
+ * then runs over p, p^2, q, q^2 (about 3-4x fewer multiply-adds, bit-identical results): decrypt() through
+ * L_p(c^(p-1) mod p^2), randomize() through rho^N = CRT((rho mod p)^(q mod p-1) lifted by ^p mod p^2, ...).
+ * Implies scb_paillier_set_private (lambda, mu are not needed).  scb_set_option(SCB_OPT_PAILLIER_CRT, 0)
+ * switches back to the public formulas (c^lambda mod N^2, rho^N mod N^2) when those were loaded too.     */
+int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t* q, int kP);
+enum { SCB_OPT_PAILLIER_CRT = 1 };
+int scb_set_option(scb_ctx* ctx, int option, int value);
 /* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1
  * (unsafe_encrypt(-1, apply_encoding=False), initiator.py:460; pow_mod gives g^-1 mod n); u_bits = bit
  * length of u (blinding exponents are < u); l = comparison bit length; rand_bits = bit length of the

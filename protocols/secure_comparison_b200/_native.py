@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscb200.so")
 
+OPT_PAILLIER_CRT = 1
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 
 MOD_PAILLIER_N2, MOD_PAILLIER_N, MOD_DGK_N, MOD_DGK_P = 0, 1, 2, 3
@@ -47,6 +48,8 @@ _SIGNATURES = {
     "scb_fixed_base_exp_dev": ([_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_paillier_set_public": ([_vp, _vp, ctypes.c_int], ctypes.c_int),
     "scb_paillier_set_private": ([_vp, _vp, ctypes.c_int, _vp], ctypes.c_int),
+    "scb_paillier_set_private_crt": ([_vp, _vp, _vp, ctypes.c_int], ctypes.c_int),
+    "scb_set_option": ([_vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_dgk_set_public": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_dgk_set_private": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_paillier_encrypt": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),

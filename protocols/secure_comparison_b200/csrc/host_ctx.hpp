@@ -13,7 +13,7 @@ struct KeysDev;
 }  // namespace scb
 
 struct scb_ctx {
-  static constexpr int NSCRATCH = 8;
+  static constexpr int NSCRATCH = 10;
   static constexpr int NFB = 4;
 
   struct Mod {
@@ -45,6 +45,10 @@ struct scb_ctx {
   int paillier_lambda_bits = 0, dgk_vp_bits = 0, dgk_rand_bits = 0;
   uint32_t* secret_dev = nullptr;     // lambda words followed by mu words
   uint32_t* vp_dev = nullptr;         // v_p words
+  // Paillier CRT form: device exponents [e1p, p, p-1, e1q, q, q-1] (kP words each) and their bit lengths
+  bool have_paillier_crt = false, use_crt = true;
+  uint32_t* crt_exp_dev = nullptr;
+  int crt_e1_bits[2] = {0, 0}, crt_P_bits[2] = {0, 0};
 
   // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the previous event
   bool profiling = false;
@@ -60,6 +64,8 @@ int fail(scb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what);
 int config_K_for_bits(int bits);
 int modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+// shared-exponent modexp with a base of kbase words (up to twice the modulus width) and kout-word results
+int modexp_dev_ex(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, int exp_bits, uint32_t* out, int kout, size_t B);
 // out[i] = a[i*a_stride..] * b[i*b_stride..] mod n (stride 0 broadcasts an operand); device pointers
 int modmul_dev_strided(scb_ctx* ctx, int slot, const uint32_t* a, size_t a_stride, const uint32_t* b, size_t b_stride, uint32_t* out, size_t B);
 }  // namespace scb

@@ -64,6 +64,23 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
   }
 }
 
+// dst = x~ (Montgomery form, lazy, < 4n) of the value x stored in `kw` words at `words`; x may be up to twice
+// as wide as the modulus (x < 2^(58K)): x = lo + hi*R with K-digit halves, x*R = mm(lo, R^2) + mm(hi, R^3).
+// Used for c mod p^2 / rho mod p in the KeyHolder's CRT paths and c mod p in is_zero.  The branch is on
+// launch-uniform values only (mm shuffles across the whole warp).
+template <int L, int TPI>
+__device__ __forceinline__ void load_mont(const Grp<L, TPI>& g, uint32_t* dst, uint32_t* tmp, const uint32_t* __restrict__ words, int kw) {
+  constexpr int K = Geo<L, TPI>::K;
+  words_to_digits(g, dst, words, kw);
+  mm<L, TPI>(g.m, g.sm, dst, dst, g.m->r2);
+  if (32 * kw > W * K) {
+#pragma unroll
+    for (int i = 0; i < L; i++) tmp[g.t * L + i] = digit_from_words(words, kw, K + g.t * L + i);
+    mm<L, TPI>(g.m, g.sm, tmp, tmp, g.m->r3);
+    lazy_add(g, dst, dst, tmp);
+  }
+}
+
 // scratch slots of one group in k_modexp: X, ACC, TMP, then the window table
 template <int L, int TPI>
 __host__ __device__ constexpr size_t modexp_scratch_words(int wbits) {
@@ -90,8 +107,7 @@ k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, in
     size_t inst = rd * total + slot;
     const bool active = inst < B;
     if (!active) inst = B - 1;
-    words_to_digits(g, TMP, base + inst * kbase, kbase);
-    mm<L, TPI>(m, g.sm, X, TMP, m->r2);                         // x~ = x*R
+    load_mont(g, X, TMP, base + inst * kbase, kbase);            // x~ = x*R (reduces double-width bases)
     group_modexp(g, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
     if (mul_in != nullptr) {
       words_to_digits(g, TMP, mul_in + inst * kout, kout);

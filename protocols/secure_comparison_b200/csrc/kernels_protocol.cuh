@@ -29,7 +29,12 @@ struct KeysDev {
   uint32_t c_sa[2][2][MAXK];    // [s == -1][alpha_i] : (enc(s) * enc(alpha_i))~   (initiator.py:459-476)
   // ---- DGK secret part ----
   int kp;                       // words of p
-  uint32_t split_r2[MAXK];      // R_p^2 * 2^(32*kp) mod p : brings the high half of c into Montgomery form mod p
+  // ---- Paillier secret part, CRT form (KeyHolder only; scb_paillier_set_private_crt) ----
+  int kP;                       // words of the Paillier primes p, q (= kN / 2)
+  uint32_t Pw[2][MAXW / 4 + 2]; // p, q
+  uint32_t Pinv32[2];           // p^-1, q^-1 mod 2^32 (exact division in L_p, L_q)
+  uint32_t crt_enc[2][MAXK];    // (q^2 (q^-2 mod p^2)) R^2, (p^2 (p^-2 mod q^2)) R^2 mod N^2   (digits of the N^2 configuration)
+  uint32_t crt_dec[2][MAXK];    // (h_p q (q^-1 mod p)) R^2, (h_q p (p^-1 mod q)) R^2 mod N        (digits of the N configuration)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -657,6 +662,104 @@ k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys,
 }
 
 // ------------------------------------------------------------------------------------------------
+// KeyHolder-side Paillier with the factorisation (CRT over p^2, q^2): same results as the public formulas.
+//   randomizer  rho^N mod N^2 :  b_P = (rho mod P)^(Q mod (P-1)) mod P,  s_P = b_P^P mod P^2   (P, Q) in {(p, q), (q, p)}
+//                                rho^N = s_p * A + s_q * B mod N^2,  A = q^2 (q^-2 mod p^2), B = p^2 (p^-2 mod q^2)
+//     ((rho mod p + k p)^p = (rho mod p)^p mod p^2, and rho^q mod p only needs the exponent mod p - 1.)
+//   decryption  m = L_p(c^(p-1) mod p^2) h_p A' + L_q(c^(q-1) mod q^2) h_q B' mod N,  L_P(x) = (x - 1) / P,
+//                                h_p = (-q)^-1 mod p,  A' = q (q^-1 mod p)   (and symmetrically)
+// The exponentiations run in k_modexp on the p / p^2 / q / q^2 moduli; the kernels here recombine.
+// ------------------------------------------------------------------------------------------------
+// out[i] = (s_p[i] * A + s_q[i] * B) * (1 + plain[i] * N) mod N^2.   s_p, s_q: [M][kN] words; plain: [M][kN]; out: [M][2kN].
+template <int L, int TPI>
+__global__ void SCB_GROUP_BOUNDS(L)
+k_crt_encrypt_combine(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ sp,
+                      const uint32_t* __restrict__ sq, const uint32_t* __restrict__ plain, uint32_t* scratch, uint32_t* __restrict__ out, size_t M) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  const int kN = keys->kN;
+  uint32_t* A = scratch + slot * 2 * K;
+  uint32_t* T = A + K;
+  const size_t rounds = (M + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t i = rd * total + slot;
+    const bool active = i < M;
+    if (!active) i = M - 1;
+    words_to_digits(g, A, sp + i * kN, kN);
+    mm<L, TPI>(m, g.sm, A, A, keys->crt_enc[0]);            // (s_p A) R
+    words_to_digits(g, T, sq + i * kN, kN);
+    mm<L, TPI>(m, g.sm, T, T, keys->crt_enc[1]);            // (s_q B) R
+    lazy_add(g, A, A, T);                                    // (rho^N) R
+    group_paillier_encode(g, keys, T, plain + i * kN, kN);   // (1 + m N) R
+    mm<L, TPI>(m, g.sm, A, A, T);
+    mm<L, TPI>(m, g.sm, A, A, m->unit);
+    canonical_store(g, A, out + i * 2 * kN, 2 * kN, active);
+  }
+}
+
+// Lq[i][h] = (y_h[i] - 1) / P_h exactly (y = 1 mod P), Hensel division in radix 2^32.  y: [2][M][kN] words, Lq: [2][M][kP].
+static __global__ void __launch_bounds__(64) k_crt_L(const KeysDev* __restrict__ keys, const uint32_t* __restrict__ y, uint32_t* __restrict__ Lq, size_t M) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= 2 * M) return;
+  const int h = idx >= M ? 1 : 0;
+  const int kP = keys->kP, kN = keys->kN;
+  uint32_t t[MAXW / 4 + 2];
+  const uint32_t* yi = y + idx * kN;
+  const uint32_t* __restrict__ Pw = keys->Pw[h];
+  uint32_t borrow = 1;
+  for (int i = 0; i < kP; i++) {
+    const uint32_t v = yi[i];
+    t[i] = v - borrow;
+    borrow = (v < borrow) ? 1u : 0u;
+  }
+  const uint32_t pinv = keys->Pinv32[h];
+  for (int j = 0; j < kP; j++) {
+    const uint32_t qj = t[j] * pinv;
+    Lq[idx * kP + j] = qj;
+    uint64_t carry = 0;
+    for (int i = 0; i + j < kP; i++) {
+      const uint64_t prod = static_cast<uint64_t>(qj) * Pw[i] + carry;
+      const uint32_t lo = static_cast<uint32_t>(prod);
+      carry = prod >> 32;
+      const uint32_t old = t[i + j];
+      t[i + j] = old - lo;
+      carry += (old < lo) ? 1u : 0u;
+    }
+  }
+}
+
+// out[i] = Lp[i] * C_p + Lq[i] * C_q mod N   (one group per element, N configuration).  Lq: [2][M][kP]; out: [M][kN].
+template <int L, int TPI>
+__global__ void SCB_GROUP_BOUNDS(L)
+k_crt_decrypt_combine(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ Lq, uint32_t* scratch,
+                      uint32_t* __restrict__ out, size_t M) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot(), total = GI::total();
+  const int kN = keys->kN, kP = keys->kP;
+  uint32_t* A = scratch + slot * 2 * K;
+  uint32_t* T = A + K;
+  const size_t rounds = (M + total - 1) / total;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t i = rd * total + slot;
+    const bool active = i < M;
+    if (!active) i = M - 1;
+    words_to_digits(g, A, Lq + i * kP, kP);
+    mm<L, TPI>(m, g.sm, A, A, keys->crt_dec[0]);
+    words_to_digits(g, T, Lq + (M + i) * kP, kP);
+    mm<L, TPI>(m, g.sm, T, T, keys->crt_dec[1]);
+    lazy_add(g, A, A, T);
+    mm<L, TPI>(m, g.sm, A, A, m->unit);
+    canonical_store(g, A, out + i * kN, kN, active);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // DGK is_zero: flag = (c^{v_p} mod p == 1)   (keyholder.py:249 -> dgk.is_zero)
 // ------------------------------------------------------------------------------------------------
 template <int L, int TPI>
@@ -668,7 +771,7 @@ k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ key
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(mp, GI::warp_smem(smem));
   const size_t slot = GI::slot(), total = GI::total();
-  const int kn = keys->kn, kp = keys->kp;
+  const int kn = keys->kn;
   uint32_t* X = scratch + slot * modexp_scratch_words<L, TPI>(wbits);
   uint32_t* ACC = X + K;
   uint32_t* TMP = ACC + K;
@@ -678,12 +781,7 @@ k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ key
     size_t i = rd * total + slot;
     const bool active = i < M;
     if (!active) i = M - 1;
-    // c mod p in Montgomery form: c = hi * 2^(32 kp) + lo
-    words_to_digits(g, X, c + i * kn, kp);
-    mm<L, TPI>(mp, g.sm, X, X, mp->r2);
-    words_to_digits(g, TMP, c + i * kn + kp, kn - kp);
-    mm<L, TPI>(mp, g.sm, TMP, TMP, keys->split_r2);
-    lazy_add(g, X, X, TMP);
+    load_mont(g, X, TMP, c + i * kn, kn);                        // (c mod p)~ from the double-width c
     group_modexp(g, ACC, X, vp, vp_words, vp_bits, wbits, table);
     mm<L, TPI>(mp, g.sm, TMP, ACC, mp->unit);
     stage_from(g, TMP);

@@ -138,6 +138,7 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   if (ctx->keys_dev) cudaFree(ctx->keys_dev);
   if (ctx->secret_dev) cudaFree(ctx->secret_dev);
   if (ctx->vp_dev) cudaFree(ctx->vp_dev);
+  if (ctx->crt_exp_dev) cudaFree(ctx->crt_exp_dev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -235,8 +236,8 @@ int window_bits_for(int ebits) {
 }
 
 template <int L, int TPI>
-int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, const uint32_t* exp, int ewords, size_t estride, int ebits,
-                  const uint32_t* mul_in, uint32_t* out, size_t B) {
+int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, int kbase, const uint32_t* exp, int ewords, size_t estride, int ebits,
+                  const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   using G = Geo<L, TPI>;
   const int wbits = window_bits_for(ebits);
   const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
@@ -245,8 +246,8 @@ int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, co
   void* scratch = nullptr;
   int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * modexp_scratch_words<L, TPI>(wbits) * sizeof(uint32_t), &scratch);
   if (rc) return rc;
-  k_modexp<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, base, md.k32, exp, ewords, estride, ebits, wbits,
-                                                               static_cast<uint32_t*>(scratch), mul_in, out, md.k32, B);
+  k_modexp<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, base, kbase, exp, ewords, estride, ebits, wbits,
+                                                               static_cast<uint32_t*>(scratch), mul_in, out, kout, B);
   return ctx->launched("k_modexp");
 }
 
@@ -396,7 +397,17 @@ extern "C" int scb_modexp_dev(scb_ctx* ctx, int slot, const uint32_t* base, cons
   if (!base || !exp || !out || exp_words <= 0 || exp_bits < 0 || exp_bits > exp_words * 32) return fail(ctx, SCB_EINVAL, "scb_modexp: bad argument");
   const scb_ctx::Mod& md = ctx->mod[slot];
   const size_t estride = exp_shared ? 0 : static_cast<size_t>(exp_words);
-#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, exp, exp_words, estride, exp_bits, mul_in, out, B)
+#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, md.k32, exp, exp_words, estride, exp_bits, mul_in, out, md.k32, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
+// base: [B][kbase] words (kbase up to twice the modulus width: reduced on load); out: [B][kout] words
+int scb::modexp_dev_ex(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, int exp_bits,
+                       uint32_t* out, int kout, size_t B) {
+  const scb_ctx::Mod& md = ctx->mod[slot];
+  if (32 * kbase > 2 * W * md.K || kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp_dev_ex: operand width out of range");
+#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, kbase, exp, exp_words, 0, exp_bits, nullptr, out, kout, B)
   SCB_DISPATCH_K(md.K, CALL)
 #undef CALL
 }

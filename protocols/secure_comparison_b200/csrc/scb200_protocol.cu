@@ -15,7 +15,7 @@ namespace {
 constexpr int INV_CHUNK = 32;
 
 // scratch buffer roles (scb_ctx::scratch indices)
-enum { SC_GROUP = 0, SC_SMALL = 1, SC_STAGE = 2, SC_INV_VP = 3, SC_INV_SMALL = 4, SC_PHASE = 5, SC_STEP4 = 6, SC_DIGITS = 7 };
+enum { SC_GROUP = 0, SC_SMALL = 1, SC_STAGE = 2, SC_INV_VP = 3, SC_INV_SMALL = 4, SC_PHASE = 5, SC_STEP4 = 6, SC_DIGITS = 7, SC_CRT = 8 };
 
 int window_bits_for(int ebits) {
   if (ebits <= 6) return 1;
@@ -233,6 +233,7 @@ extern "C" int scb_paillier_set_public(scb_ctx* ctx, const uint32_t* n, int kN) 
   if (rc) return rc;
   ctx->have_paillier_pub = true;
   ctx->have_paillier_priv = false;
+  ctx->have_paillier_crt = false;
   return upload_keys(ctx);
 }
 
@@ -314,18 +315,8 @@ extern "C" int scb_dgk_set_private(scb_ctx* ctx, const uint32_t* p, int kp, cons
   rc = scb_modulus_load(ctx, SCB_MOD_DGK_P, p, kp);
   if (rc) return rc;
   const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_P];
-  if (29 * md.K < 32 * kp || 29 * md.K < 32 * (hk->kn - kp))
-    return fail(ctx, SCB_EINVAL, "scb_dgk_set_private: p too short for the two-piece reduction of c mod p");
+  if (2 * W * md.K < 32 * hk->kn) return fail(ctx, SCB_EINVAL, "scb_dgk_set_private: p too short for the double-width reduction of c mod p");
   hk->kp = kp;
-  // split_r2 = (2^(32 kp))~ * R = mm(2^(32 kp), R^3)
-  std::vector<uint32_t> two(kp + 1, 0);
-  two[kp] = 1;
-  memset(hk->split_r2, 0, sizeof(hk->split_r2));
-#define CALL(L, TPI) const_to_mont<L, TPI>(ctx, md, two.data(), kp + 1, 1, 1, hk->split_r2)
-  auto run = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
-#undef CALL
-  rc = run();
-  if (rc) return rc;
   ctx->dgk_vp.assign(v_p, v_p + vp_words);
   ctx->dgk_vp_bits = vp_bits;
   if (ctx->vp_dev) cudaFree(ctx->vp_dev);
@@ -335,6 +326,175 @@ extern "C" int scb_dgk_set_private(scb_ctx* ctx, const uint32_t* p, int kp, cons
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "upload v_p");
   ctx->have_dgk_priv = true;
+  return upload_keys(ctx);
+}
+
+extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
+  if (!ctx) return SCB_EINVAL;
+  switch (option) {
+    case SCB_OPT_PAILLIER_CRT: ctx->use_crt = value != 0; return SCB_OK;
+    default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Paillier secret key in CRT form (KeyHolder)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef std::vector<uint32_t> HW;   // little-endian words, host side; only used once per key
+
+HW hw_mul(const HW& a, const HW& b) {
+  HW r(a.size() + b.size(), 0);
+  for (size_t i = 0; i < a.size(); i++) {
+    uint64_t carry = 0;
+    for (size_t j = 0; j < b.size(); j++) {
+      const uint64_t t = static_cast<uint64_t>(a[i]) * b[j] + r[i + j] + carry;
+      r[i + j] = static_cast<uint32_t>(t);
+      carry = t >> 32;
+    }
+    r[i + b.size()] = static_cast<uint32_t>(carry);
+  }
+  return r;
+}
+int hw_bits(const HW& x) {
+  for (int i = static_cast<int>(x.size()) - 1; i >= 0; i--)
+    if (x[i]) return i * 32 + 32 - __builtin_clz(x[i]);
+  return 0;
+}
+bool hw_geq(const HW& a, const HW& b) {   // same length
+  for (int i = static_cast<int>(a.size()) - 1; i >= 0; i--)
+    if (a[i] != b[i]) return a[i] > b[i];
+  return true;
+}
+void hw_sub(HW& a, const HW& b) {         // a -= b (same length, a >= b)
+  uint64_t borrow = 0;
+  for (size_t i = 0; i < a.size(); i++) {
+    const uint64_t d = static_cast<uint64_t>(a[i]) - b[i] - borrow;
+    a[i] = static_cast<uint32_t>(d);
+    borrow = (d >> 63) & 1u;
+  }
+}
+bool hw_is_zero(const HW& a) {
+  for (uint32_t w : a)
+    if (w) return false;
+  return true;
+}
+// a mod m by shift-and-subtract (a one-off on 1024..4096-bit values)
+HW hw_mod(const HW& a, const HW& m) {
+  HW r(m.size() + 1, 0), mm_(m);
+  mm_.push_back(0);
+  for (int bit = hw_bits(a) - 1; bit >= 0; bit--) {
+    uint32_t carry = (a[bit >> 5] >> (bit & 31)) & 1u;
+    for (size_t i = 0; i < r.size(); i++) {
+      const uint32_t nc = r[i] >> 31;
+      r[i] = (r[i] << 1) | carry;
+      carry = nc;
+    }
+    if (hw_geq(r, mm_)) hw_sub(r, mm_);
+  }
+  r.pop_back();
+  return r;
+}
+HW hw_resized(const HW& a, size_t k) {
+  HW r(a);
+  r.resize(k, 0);
+  return r;
+}
+
+}  // namespace
+
+extern "C" int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t* q, int kP) {
+  int rc = need_keys(ctx, true, false, false, false, "scb_paillier_set_private_crt");
+  if (rc) return rc;
+  KeysDev* hk = host_keys(ctx);
+  const int kN = hk->kN;
+  if (!p || !q || kP <= 0 || 2 * kP != kN || kP > MAXW / 4) return fail(ctx, SCB_EINVAL, "scb_paillier_set_private_crt: p and q must have kN/2 words each");
+  const HW P[2] = {HW(p, p + kP), HW(q, q + kP)};
+  const HW Nw(hk->Nw, hk->Nw + kN);
+  if (hw_mul(P[0], P[1]) != Nw) return fail(ctx, SCB_EINVAL, "scb_paillier_set_private_crt: p * q != N");
+  const HW P2[2] = {hw_mul(P[0], P[0]), hw_mul(P[1], P[1])};   // kN words each
+  const int slotP[2] = {SCB_MOD_PAILLIER_P, SCB_MOD_PAILLIER_Q}, slotP2[2] = {SCB_MOD_PAILLIER_P2, SCB_MOD_PAILLIER_Q2};
+  for (int h = 0; h < 2; h++) {
+    if ((rc = scb_modulus_load(ctx, slotP[h], P[h].data(), kP))) return rc;
+    if ((rc = scb_modulus_load(ctx, slotP2[h], P2[h].data(), kN))) return rc;
+    if (2 * W * ctx->mod[slotP[h]].K < 32 * kN || 2 * W * ctx->mod[slotP2[h]].K < 64 * kN)
+      return fail(ctx, SCB_EINVAL, "scb_paillier_set_private_crt: primes too short for the double-width reductions");
+  }
+  // exponents: e1[h] = Q mod (P - 1) (P - 1 when that is 0), P (for the lift b^P mod P^2), P - 1 (decryption)
+  HW exps;                       // 6 arrays of kP words: e1p, p, p-1, e1q, q, q-1
+  int e1_bits[2], P_bits[2];
+  for (int h = 0; h < 2; h++) {
+    HW pm1(P[h]);
+    pm1[0] -= 1;                 // P is odd
+    HW e1 = hw_mod(P[1 - h], pm1);
+    if (hw_is_zero(e1)) e1 = pm1;
+    e1_bits[h] = hw_bits(e1);
+    P_bits[h] = hw_bits(P[h]);
+    exps.insert(exps.end(), e1.begin(), e1.end());
+    exps.insert(exps.end(), P[h].begin(), P[h].end());
+    exps.insert(exps.end(), pm1.begin(), pm1.end());
+  }
+  if (ctx->crt_exp_dev) cudaFree(ctx->crt_exp_dev);
+  cudaError_t e = cudaMalloc(&ctx->crt_exp_dev, sizeof(uint32_t) * exps.size());
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(crt exponents)");
+  e = cudaMemcpyAsync(ctx->crt_exp_dev, exps.data(), sizeof(uint32_t) * exps.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "upload crt exponents");
+  for (int h = 0; h < 2; h++) {
+    ctx->crt_e1_bits[h] = e1_bits[h];
+    ctx->crt_P_bits[h] = P_bits[h];
+  }
+  // recombination constants, derived with the library's own batched primitives (B = 1)
+  hk->kP = kP;
+  memset(hk->Pw, 0, sizeof(hk->Pw));
+  memset(hk->crt_enc, 0, sizeof(hk->crt_enc));
+  memset(hk->crt_dec, 0, sizeof(hk->crt_dec));
+  HW enc_const, dec_const;       // 2 x 2kN words, 2 x kN words
+  for (int h = 0; h < 2; h++) {
+    memcpy(hk->Pw[h], P[h].data(), sizeof(uint32_t) * kP);
+    uint32_t inv = P[h][0];
+    for (int i = 0; i < 5; i++) inv *= 2u - P[h][0] * inv;
+    hk->Pinv32[h] = inv;
+    uint8_t ok = 0;
+    // A_h = Q^2 * (Q^-2 mod P^2) < N^2
+    HW inv2(kN, 0);
+    if ((rc = scb_modinv(ctx, slotP2[h], P2[1 - h].data(), inv2.data(), &ok, 1))) return rc;
+    HW A = hw_resized(hw_mul(P2[1 - h], inv2), 2 * kN);
+    enc_const.insert(enc_const.end(), A.begin(), A.end());
+    // C_h = h_P * Q * (Q^-1 mod P) mod N,  h_P = (-Q)^-1 mod P = P - (Q^-1 mod P)
+    HW qinv(kP, 0);
+    if ((rc = scb_modinv(ctx, slotP[h], P[1 - h].data(), qinv.data(), &ok, 1))) return rc;
+    HW hP(P[h]);
+    hw_sub(hP, qinv);
+    HW Aprime = hw_resized(hw_mul(P[1 - h], qinv), kN);       // < N
+    HW C(kN, 0);
+    HW hP_N = hw_resized(hP, kN);
+    if ((rc = scb_modmul(ctx, SCB_MOD_PAILLIER_N, Aprime.data(), hP_N.data(), C.data(), 1))) return rc;
+    dec_const.insert(dec_const.end(), C.begin(), C.end());
+  }
+  {
+    const scb_ctx::Mod& md = ctx->mod[SCB_MOD_PAILLIER_N2];
+    std::vector<uint32_t> digs(2 * MAXK);
+#define CALL(L, TPI) const_to_mont<L, TPI>(ctx, md, enc_const.data(), 2 * kN, 2, 1, digs.data())
+    auto run = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
+#undef CALL
+    if ((rc = run())) return rc;
+    memcpy(hk->crt_enc[0], digs.data(), sizeof(uint32_t) * md.K);
+    memcpy(hk->crt_enc[1], digs.data() + md.K, sizeof(uint32_t) * md.K);
+  }
+  {
+    const scb_ctx::Mod& md = ctx->mod[SCB_MOD_PAILLIER_N];
+    std::vector<uint32_t> digs(2 * MAXK);
+#define CALL(L, TPI) const_to_mont<L, TPI>(ctx, md, dec_const.data(), kN, 2, 1, digs.data())
+    auto run = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
+#undef CALL
+    if ((rc = run())) return rc;
+    memcpy(hk->crt_dec[0], digs.data(), sizeof(uint32_t) * md.K);
+    memcpy(hk->crt_dec[1], digs.data() + md.K, sizeof(uint32_t) * md.K);
+  }
+  ctx->have_paillier_crt = true;
+  ctx->have_paillier_priv = true;
   return upload_keys(ctx);
 }
 
@@ -513,11 +673,82 @@ extern "C" int scb_initiator_step1_dev(scb_ctx* ctx, const uint32_t* x, const ui
 #undef CALL
 }
 
+namespace {
+
+template <int L, int TPI>
+int phase_crt_encrypt_combine(scb_ctx* ctx, const uint32_t* sp, const uint32_t* sq, const uint32_t* plain, uint32_t* out, size_t M) {
+  using C = Cfg<L, TPI>;
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_PAILLIER_N2];
+  const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_crt_encrypt_combine<L, TPI>), C::SMEM, M, C::GPB);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * 2 * C::K, &scratch);
+  if (rc) return rc;
+  k_crt_encrypt_combine<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, sp, sq, plain, static_cast<uint32_t*>(scratch), out, M);
+  return ctx->launched("k_crt_encrypt_combine");
+}
+
+template <int L, int TPI>
+int phase_crt_decrypt_combine(scb_ctx* ctx, const uint32_t* Lq, uint32_t* out, size_t M) {
+  using C = Cfg<L, TPI>;
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_PAILLIER_N];
+  const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_crt_decrypt_combine<L, TPI>), C::SMEM, M, C::GPB);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * 2 * C::K, &scratch);
+  if (rc) return rc;
+  k_crt_decrypt_combine<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, Lq, static_cast<uint32_t*>(scratch), out, M);
+  return ctx->launched("k_crt_decrypt_combine");
+}
+
+// KeyHolder with the factorisation: (1 + m N) * rho^N mod N^2 through p, p^2, q, q^2 (see kernels_protocol.cuh)
+int paillier_encrypt_crt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M) {
+  const KeysDev* hk = host_keys(ctx);
+  const int kN = hk->kN, kP = hk->kP;
+  Arena ph;
+  int rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * M * kP) + 2 * pad256(sizeof(uint32_t) * M * kN), &ph);
+  if (rc) return rc;
+  uint32_t* b = ph.take<uint32_t>(M * kP);
+  uint32_t* s[2] = {ph.take<uint32_t>(M * kN), ph.take<uint32_t>(M * kN)};
+  const int slotP[2] = {SCB_MOD_PAILLIER_P, SCB_MOD_PAILLIER_Q}, slotP2[2] = {SCB_MOD_PAILLIER_P2, SCB_MOD_PAILLIER_Q2};
+  for (int h = 0; h < 2; h++) {
+    const uint32_t* ex = ctx->crt_exp_dev + static_cast<size_t>(3 * h) * kP;
+    if ((rc = scb::modexp_dev_ex(ctx, slotP[h], rho, kN, ex, kP, ctx->crt_e1_bits[h], b, kP, M))) return rc;          // (rho mod P)^(Q mod (P-1)) mod P
+    if ((rc = scb::modexp_dev_ex(ctx, slotP2[h], b, kP, ex + kP, kP, ctx->crt_P_bits[h], s[h], kN, M))) return rc;    // b^P mod P^2
+  }
+  const int K = ctx->mod[SCB_MOD_PAILLIER_N2].K;
+#define CALL(L, TPI) phase_crt_encrypt_combine<L, TPI>(ctx, s[0], s[1], plain, out, M)
+  SCB_DISPATCH_K(K, CALL)
+#undef CALL
+}
+
+int paillier_decrypt_crt(scb_ctx* ctx, const uint32_t* c, uint32_t* out, size_t M) {
+  const KeysDev* hk = host_keys(ctx);
+  const int kN = hk->kN, kP = hk->kP;
+  Arena ph;
+  int rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * 2 * M * kN) + pad256(sizeof(uint32_t) * 2 * M * kP), &ph);
+  if (rc) return rc;
+  uint32_t* y = ph.take<uint32_t>(2 * M * kN);
+  uint32_t* Lq = ph.take<uint32_t>(2 * M * kP);
+  const int slotP2[2] = {SCB_MOD_PAILLIER_P2, SCB_MOD_PAILLIER_Q2};
+  for (int h = 0; h < 2; h++) {
+    const uint32_t* ex = ctx->crt_exp_dev + static_cast<size_t>(3 * h + 2) * kP;
+    if ((rc = scb::modexp_dev_ex(ctx, slotP2[h], c, 2 * kN, ex, kP, ctx->crt_P_bits[h], y + static_cast<size_t>(h) * M * kN, kN, M))) return rc;   // c^(P-1) mod P^2
+  }
+  k_crt_L<<<static_cast<unsigned>((2 * M + 63) / 64), 64, 0, ctx->stream>>>(ctx->keys_dev, y, Lq, M);
+  if ((rc = ctx->launched("k_crt_L"))) return rc;
+  const int K = ctx->mod[SCB_MOD_PAILLIER_N].K;
+#define CALL(L, TPI) phase_crt_decrypt_combine<L, TPI>(ctx, Lq, out, M)
+  SCB_DISPATCH_K(K, CALL)
+#undef CALL
+}
+
+}  // namespace
+
 extern "C" int scb_paillier_encrypt_dev(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M) {
   int rc = need_keys(ctx, true, false, false, false, "scb_paillier_encrypt");
   if (rc) return rc;
   if (M == 0) return SCB_OK;
   if (!plain || !out) return fail(ctx, SCB_EINVAL, "scb_paillier_encrypt: null pointer");
+  if (rho != nullptr && ctx->have_paillier_crt && ctx->use_crt) return paillier_encrypt_crt(ctx, plain, rho, out, M);
   const int K = ctx->mod[SCB_MOD_PAILLIER_N2].K;
 #define CALL(L, TPI) phase_paillier_encrypt<L, TPI>(ctx, plain, rho, out, M)
   SCB_DISPATCH_K(K, CALL)
@@ -529,9 +760,11 @@ extern "C" int scb_paillier_decrypt_dev(scb_ctx* ctx, const uint32_t* c, uint32_
   if (rc) return rc;
   if (M == 0) return SCB_OK;
   if (!c || !out) return fail(ctx, SCB_EINVAL, "scb_paillier_decrypt: null pointer");
+  if (ctx->have_paillier_crt && ctx->use_crt) return paillier_decrypt_crt(ctx, c, out, M);
+  if (ctx->paillier_lambda.empty()) return fail(ctx, SCB_ESTATE, "scb_paillier_decrypt: lambda / mu not loaded (and the CRT path is disabled)");
   const int kN = host_keys(ctx)->kN, kc = 2 * kN;
   Arena ph;
-  rc = get_arena(ctx, SC_PHASE, pad256(sizeof(uint32_t) * M * kc) + pad256(sizeof(uint32_t) * M * kN), &ph);
+  rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * M * kc) + pad256(sizeof(uint32_t) * M * kN), &ph);
   if (rc) return rc;
   uint32_t* xw = ph.take<uint32_t>(M * kc);
   uint32_t* qw = ph.take<uint32_t>(M * kN);

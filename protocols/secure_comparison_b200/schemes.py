@@ -30,6 +30,23 @@ def _raw(ct) -> int:
     raise TypeError(f"cannot read a raw ciphertext value from {type(ct).__name__}")
 
 
+def _paillier_primes(sk, n: int, lam: int):
+    """(p, q) of a Paillier secret key, or None when they cannot be recovered (lambda = lcm variants)."""
+    import math
+    p, q = getattr(sk, "p", None), getattr(sk, "q", None)
+    if p is not None and q is not None and int(p) * int(q) == n:
+        return int(p), int(q)
+    s = n + 1 - lam                      # p + q when lambda = (p - 1)(q - 1)
+    disc = s * s - 4 * n
+    if disc < 0:
+        return None
+    root = math.isqrt(disc)
+    if root * root != disc or (s + root) % 2:
+        return None
+    p, q = (s + root) // 2, (s - root) // 2
+    return (p, q) if p * q == n and q > 1 else None
+
+
 def as_limbs(values, k: int) -> np.ndarray:
     """Batch container -> ``[..][k]`` uint32 limbs.  Accepts limb arrays (returned as is), a single
     ciphertext / int (batch of one), or (nested) sequences of ciphertexts / ints."""
@@ -70,6 +87,7 @@ class SchemeEngine(Engine):
         self.rand_words = 0
         self.rb_words = 0
         self.has_paillier_secret = False
+        self.has_paillier_crt = False
         self.has_dgk_secret = False
 
     # ------------------------------------------------------------------ keys
@@ -93,6 +111,16 @@ class SchemeEngine(Engine):
             lam_w, mu_w = int_to_limbs(lam, lw), int_to_limbs(mu, self.kN)
             self._check(self.lib.scb_paillier_set_private(self.ctx, nat._ptr(lam_w), lw, nat._ptr(mu_w)))
             self.has_paillier_secret = True
+            # CRT form for the KeyHolder's Paillier work (decrypt, randomize): needs the primes.  The upstream
+            # secret key stores (lambda_, mu, n); with lambda = (p-1)(q-1) the primes are the roots of
+            # X^2 - (N + 1 - lambda) X + N.  A one-off key-setup computation, like key generation itself.
+            pq = _paillier_primes(sk, n, lam)
+            self.has_paillier_crt = False
+            if pq is not None and self.kN % 2 == 0 and all(limbs_for_bits(v.bit_length()) <= self.kN // 2 for v in pq):
+                kP = self.kN // 2
+                p_w, q_w = int_to_limbs(pq[0], kP), int_to_limbs(pq[1], kP)
+                self._check(self.lib.scb_paillier_set_private_crt(self.ctx, nat._ptr(p_w), nat._ptr(q_w), kP))
+                self.has_paillier_crt = True
 
     def load_dgk(self, scheme, l: int, rand_bits: Optional[int] = None) -> None:
         pk = scheme.public_key
@@ -121,6 +149,11 @@ class SchemeEngine(Engine):
             self._check(self.lib.scb_dgk_set_private(self.ctx, nat._ptr(p_w), kp, nat._ptr(vp_w), vw, v_p.bit_length()))
             self._moduli[nat.MOD_DGK_P] = (p, kp)
             self.has_dgk_secret = True
+
+    def set_paillier_crt(self, enabled: bool) -> None:
+        """Switch the KeyHolder's Paillier work between the CRT form (default when the primes are known) and the
+        public formulas c^lambda mod N^2 / rho^N mod N^2.  Results are bit-identical either way."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_PAILLIER_CRT, int(bool(enabled))))
 
     # ------------------------------------------------------------------ scheme operations (host buffers)
     def paillier_encrypt(self, plain: np.ndarray, rho: Optional[np.ndarray] = None) -> np.ndarray:

@@ -48,6 +48,29 @@ def test_paillier_decrypt(setup):
     assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want
 
 
+def test_paillier_crt_and_public_formulas_agree(setup):
+    """KeyHolder-side CRT (p, p^2, q, q^2) vs the public formulas c^lambda mod N^2 / rho^N mod N^2: identical bits."""
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    assert eng.has_paillier_crt
+    B = 33
+    m = [rng.randrange(N) for _ in range(B)]
+    m[:3] = [0, 1, N - 1]
+    rho = [rng.randrange(1, N) for _ in range(B)]
+    rho[:3] = [1, N - 1, paillier.secret_key.p]             # a multiple of p: the lift (rho mod p)^... = 0 mod p^2
+    want = [(1 + v * N) * pow(r, N, N2) % N2 for v, r in zip(m, rho)]
+    c = [rng.randrange(1, N2) for _ in range(B)]
+    want_dec = [oracle.paillier_decrypt_raw(v) for v in c]
+    try:
+        for crt in (True, False):
+            eng.set_paillier_crt(crt)
+            got = eng.paillier_encrypt(ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN))
+            assert limbs_to_ints(got) == want, f"encrypt+randomize, crt={crt}"
+            assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want_dec, f"decrypt, crt={crt}"
+    finally:
+        eng.set_paillier_crt(True)
+
+
 def test_step1_pieces(setup):
     paillier, dgk, l, eng, oracle, rng = setup
     N, N2 = paillier.public_key.n, paillier.public_key.n_squared
