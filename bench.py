@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """bench.py -- secure comparisons/s of the batched DGK/Veugen protocol on B200 (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 3 --warmup 3                    # our arm (CUDA engine)
-    python bench.py --impl reference --steps 1 --warmup 1            # CPU reference arm (oracle port, GMP)
+    python bench.py --gpus 1 --steps 2 --warmup 3                    # our arm (CUDA engine)
+    python bench.py --impl reference --steps 1 --warmup 1            # CPU reference arm (oracle port over GMP)
     python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...
 
 One "step" = one pass of the whole protocol (all five party-phases: A1 step_1+randomize, B1 decrypt +
@@ -10,13 +10,16 @@ steps 4a/4b+randomize, A2 steps 3,4c-4i+randomize, B2 steps 4j,5+randomize, A3 s
 batch of B comparisons with synthetic seeded inputs and host-supplied nonces.  Workload at N=1:
 BASELINE.json configs[1]: B = 65,536, l = 16, Paillier-2048 / DGK-2048 (v = 160).  Multi-GPU: the batch
 shards by comparison index, one process + one context per GPU, no collective on the data path (weak
-scaling: B per GPU is fixed).
+scaling: B per GPU is fixed; NCCL only carries the barrier and the max-over-ranks of the timings).
 
-`value`  : comparisons/s with every input resident in HBM (device-pointer C-ABI entry points), CUDA
-           events on the engine's stream, max over ranks.
-`e2e`    : the same through the host-buffer C-ABI calls (pinned host buffers; H2D of every input and D2H
-           of every message/result inside the timed region).
-`roofline`: integer-multiply pipe (IMAD.WIDE.U32), not HBM / tensor: see DESIGN.md section "Roofline".
+`value`   : comparisons/s with every input resident in HBM (device-pointer C-ABI entry points), CUDA
+            events on the engine's stream, max over ranks.
+`e2e`     : the same through the host-buffer C-ABI calls (pinned host inputs; H2D of every input and D2H
+            of every message/result inside the timed region).
+`roofline`: integer-multiply pipe (IMAD.WIDE.U32 on the fmaheavy pipe), not HBM / tensor: DESIGN.md "Roofline".
+
+The product path never touches ``oracle/``: keys come from a key file through the package's own loader.
+``oracle`` is imported only by the ``cpu_baseline`` leg and by ``--impl reference``.
 """
 from __future__ import annotations
 
@@ -33,10 +36,19 @@ sys.path.insert(0, ROOT)
 
 METRIC = "secure comparisons/sec (Paillier-2048/DGK-2048, l=16)"
 UNIT = "comparisons/s"
-# measured on this pool's B200 (profiles/r01_imad_microbench2.jsonl): IMAD.WIDE.U32 issues at 32 lanes/clk/SM
+KEY_FILE = os.path.join(ROOT, "tests", "golden", "keys_p2048_d2048_v160_l16.json")   # seeded synthetic key pair (data)
+# Integer-multiply peak: IMAD.WIDE.U32 (32x32+64 -> 64) issues on the fmaheavy pipe only, 8 lanes/clk/SMSP =
+# 32 MAC/clk/SM (ncu: sm__pipe_fmaheavy_cycles_active; microbenchmark profiles/r01_imad_microbench2.jsonl measured
+# 8.6 TMAC/s sustained = 29.6/clk/SM at the nominal clock).  Peak used for `frac` = 148 SMs x 32 x 1.965 GHz.
 INT_PEAK_MAC_PER_S = 148 * 32 * 1.965e9
-MAC_PER_COMPARISON_L16 = 567e6      # SURVEY.md section 8d, reference-faithful op list, 32x32->64 MAC
+INT_PEAK_MEASURED_MAC_PER_S = 8.596e12
+# SURVEY.md section 8d algorithmic work, 32x32->64 MAC units (fixed-window modexp, k 32-bit limbs: (e + e/5 + 32)(2k^2 + k))
+MAC_PER_COMPARISON_L16 = 567e6      # reference-faithful operation list of one interactive comparison
 MAC_PER_MODEXP_4096_2048 = 81.91e6  # one rho^N mod N^2 (k = 128 limbs, 2048-bit exponent)
+# fixed (x, y) pairs of the reference's tests (test_secure_comparison.py:27-37), non-negative ones
+FIXED_PAIRS = [(0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7804), (8668, 9015), (23, 42), (42, 23), (7, 7), (0, 0)]
+# ncu --set full of k_step1<18,8> at B = 32768 (profiles/r01e_ncu_k_step1.txt): dram read + write bytes per launch
+NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (4.888848e9 + 1.476549e9) / 32768
 
 
 def parse_args():
@@ -47,7 +59,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="comparisons per GPU per step")
     ap.add_argument("--l", type=int, default=16)
-    ap.add_argument("--cpu-per-core", type=int, default=6, help="comparisons per host core in the CPU sample")
+    ap.add_argument("--cpu-per-core", type=int, default=40, help="comparisons per host core in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -88,33 +100,33 @@ class ClockSampler:
     def summary(self):
         sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
         mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        pw = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
         reasons = set()
         for s in self.samples:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------- workload
-def make_workload(B: int, l: int, seed: int, eng, paillier):
+def make_workload(B: int, l: int, seed: int, eng):
     """Seeded synthetic batch: plaintext pairs, nonces (host numpy), input ciphertexts made on the GPU (untimed)."""
     import numpy as np
-
-    from oracle.workload import REFERENCE_PAIRS   # fixed (x, y) pairs of the reference's tests; data only
 
     rng = np.random.default_rng(seed)
     x = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
     y = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
-    fixed = [(a, b) for a, b in REFERENCE_PAIRS if a >= 0] + [(23, 42), (42, 23), (7, 7), (0, 0), ((1 << l) - 1, (1 << l) - 1)]
+    fixed = FIXED_PAIRS + [((1 << l) - 1, (1 << l) - 1)]
     for i, (a, b) in enumerate(fixed[:B]):
         x[i], y[i] = a, b
-    kN, kn = eng.kN, eng.kn
+    kN = eng.kN
 
     def rand_limbs(shape, top_mask=0x7FFFFFFF):
         a = rng.integers(0, 1 << 32, size=shape, dtype=np.uint64).astype(np.uint32)
         a[..., -1] &= top_mask          # < 2^(32k-1) <= N: N has its top bit set
+        a[..., 0] |= 1                  # never 0
         return a
 
     def rand_bits(shape_words, bits):
@@ -136,16 +148,13 @@ def make_workload(B: int, l: int, seed: int, eng, paillier):
         plain[0, :, 1] = (x >> 32).astype(np.uint32)
         plain[1, :, 1] = (y >> 32).astype(np.uint32)
     rho_in = rand_limbs((2, B, kN))
-    rho_in[..., 0] |= 1
     enc = eng.paillier_encrypt(plain.reshape(2 * B, kN), rho_in.reshape(2 * B, kN)).reshape(2, B, 2 * kN)
     w = {
-        "x": enc[0], "y": enc[1], "r": rand_limbs((B, kN)), "rho_z": rand_limbs((B, kN)) | np.uint32(0),
+        "x": enc[0], "y": enc[1], "r": rand_limbs((B, kN)), "rho_z": rand_limbs((B, kN)),
         "delta_a": rng.integers(0, 2, size=B, dtype=np.uint8), "r_blind": r_blind, "perm": perm,
         "rho_c": rand_bits((B, l + 1, eng.rand_words), rand_bits_n), "rho_db": rand_bits((B, l + 1, eng.rand_words), rand_bits_n),
         "rho_enc3": rand_limbs((B, 3, kN)),
     }
-    w["rho_z"][:, 0] |= 1
-    w["rho_enc3"][..., 0] |= 1
     truth = (x <= y).astype(np.uint8)
     return w, truth
 
@@ -155,9 +164,10 @@ def run_ours(args):
     import numpy as np
     import torch
 
-    from oracle.workload import make_schemes     # seeded key cache (tests/golden/keys_*.json); keys are data
     from protocols.secure_comparison_b200 import SchemeEngine
     from protocols.secure_comparison_b200 import _native as nat
+    from protocols.secure_comparison_b200.keyfile import schemes_from_json
+    from protocols.secure_comparison_b200.sharding import shard_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,18 +179,20 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, l = args.batch, args.l
-    paillier, dgk = make_schemes(2048, 2048, 160, l)
+    # weak scaling: the global batch is world * B comparisons; this rank owns the contiguous block [lo, hi)
+    lo, hi = shard_range(world * B, rank, world)
+    assert hi - lo == B
+    paillier, dgk = schemes_from_json(KEY_FILE)
     eng = SchemeEngine(local)
     eng.load_paillier(paillier)
     eng.load_dgk(dgk, l)
-    w, truth = make_workload(B, l, seed=1234 + rank, eng=eng, paillier=paillier)
+    w, truth = make_workload(B, l, seed=1234 + rank, eng=eng)
     kN, kc, kn = eng.kN, eng.kc, eng.kn
     stream = torch.cuda.ExternalStream(eng.stream_ptr)
     lib, ctx = eng.lib, eng.ctx
 
     def dev(a):
-        t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
-        return t
+        return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
 
     d = {k: dev(v) for k, v in w.items()}
     i32 = dict(dtype=torch.int32, device="cuda")
@@ -242,26 +254,35 @@ def run_ours(args):
     bits = d_bit.cpu().numpy().view(np.uint32)
     bits_ok = bool(np.array_equal(bits[:, 0].astype(np.uint8), truth) and not bits[:, 1:].any())
 
-    # ---- per-kernel timing of one more step (events after every launch) for the roofline of the dominant kernel
+    # ---- per-kernel timing of one more step (one CUDA event after every launch, on the engine's stream) for the
+    #      roofline of the dominant kernel: k_step1 = B modexps rho^N mod N^2 (4096-bit modulus, 2048-bit exponent)
     eng.profile_begin()
     step_device()
     kernels = eng.profile_end()
     step_ms_prof = sum(k["ms"] for k in kernels.values())
     top_name = max(kernels, key=lambda k: kernels[k]["ms"])
-    enc = kernels.get("k_paillier_encrypt", {"ms": 0.0, "launches": 1})
-    enc_ms = enc["ms"] / max(enc["launches"], 1)
-    enc_mac = 3 * B * MAC_PER_MODEXP_4096_2048          # 3B randomizers rho^N mod N^2 per launch (+ the 1 + mN encodings, negligible)
-    achieved = enc_mac / (enc_ms * 1e-3) / 1e12 if enc_ms else 0.0
-    bytes_per_launch = 3 * B * (2 * kN * 4 + 2 * kc * 4)   # plaintext + rho in, ciphertext out (algorithmic HBM bytes)
+    k1 = kernels.get("k_step1", {"ms": 0.0, "launches": 1})
+    k1_ms = k1["ms"] / max(k1["launches"], 1)
+    k1_mac = B * MAC_PER_MODEXP_4096_2048                 # algorithmic: B randomizers rho^N mod N^2 (+ 5 products, negligible)
+    achieved = k1_mac / (k1_ms * 1e-3) / 1e12 if k1_ms else 0.0
+    bytes_per_launch = B * (2 * kc * 4 + 2 * kN * 4 + kc * 4)   # x, y, r, rho in; z_enc out (algorithmic HBM bytes)
     roofline = {
         "bound": "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy; not hbm, not tensor)",
-        "kernel": "k_paillier_encrypt", "kernel_share_of_step": round(enc["ms"] / step_ms_prof, 4) if step_ms_prof else None,
+        "kernel": "k_step1<18,8>", "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
+        "kernel_ms_per_launch": round(k1_ms, 3),
         "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic)",
         "frac": round(achieved * 1e12 / INT_PEAK_MAC_PER_S, 4),
-        "peak_source": "measured: profiles/r01_imad_microbench2.jsonl (IMAD.WIDE.U32 = 32 lanes/clk/SM x 148 SMs x 1.965 GHz)",
-        "traffic": None,
-        "hbm_gbs_algorithmic": round(bytes_per_launch / (enc_ms * 1e-3) / 1e9, 2) if enc_ms else None,
+        "peak_source": "hardware rate seen by ncu (IMAD.WIDE.U32: 32 lanes/clk/SM x 148 SMs x 1.965 GHz); the IMAD microbenchmark "
+                       "on this pool sustains 8.6 TMAC/s (profiles/r01_imad_microbench2.jsonl)",
+        "frac_of_measured_microbench_peak": round(achieved * 1e12 / INT_PEAK_MEASURED_MAC_PER_S, 4),
+        "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
+        "traffic_note": "dram bytes of one k_step1 launch scaled from the ncu capture at B=32768 (window tables of 9,472 resident groups "
+                        "exceed L2); ~12 GB/s, non-binding next to hbm_gbs",
+        "algorithmic_bytes": int(bytes_per_launch),
+        "hbm_gbs_algorithmic": round(bytes_per_launch / (k1_ms * 1e-3) / 1e9, 2) if k1_ms else None,
         "whole_step_frac": round(value / world * MAC_PER_COMPARISON_L16 / INT_PEAK_MAC_PER_S, 4),
+        "whole_step_note": "whole_step_frac counts the reference-faithful 567 M MAC per comparison; CRT on the KeyHolder side and the fixed-base "
+                           "table for h^rho do fewer (identical outputs), so it may exceed the per-kernel fraction",
         "top_kernel_by_time": top_name,
         "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -299,7 +320,7 @@ def run_ours(args):
         e2e = {"value": round(world * B * args.steps / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle as the timed CPU port, never on the product path
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import time_comparisons
@@ -312,10 +333,11 @@ def run_ours(args):
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (29-bit digits, 64-bit accumulators)",
             "data": "synthetic (seeded keys, inputs and host-supplied nonces)",
             "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-2048/DGK-2048 (v=160), interactive flow (all randomize() calls)",
-                       "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l},
+                       "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l,
+                       "sharding": "contiguous block of the global batch per rank, no data-path collective"},
             "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "modexp_4096_per_s_in_encrypt_kernel": round(3 * B / (enc_ms * 1e-3), 1) if enc_ms else None,
+            "modexp_4096_per_s_in_step1_kernel": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -334,7 +356,7 @@ def run_reference(args):
         return
     from oracle.cpu_baseline import time_comparisons
     vals = []
-    for i in range(args.warmup if args.warmup < 2 else 1):
+    for _ in range(min(args.warmup, 1)):
         time_comparisons(2048, 2048, 160, args.l, per_core=1)
     res = None
     for _ in range(args.steps):

@@ -126,7 +126,8 @@ int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t
 enum { SCB_OPT_PAILLIER_CRT = 1 };
 int scb_set_option(scb_ctx* ctx, int option, int value);
 /* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1
- * (unsafe_encrypt(-1, apply_encoding=False), initiator.py:460; pow_mod gives g^-1 mod n); u_bits = bit
+ * (unsafe_encrypt(-1, apply_encoding=False), initiator.py:460; pow_mod gives g^-1 mod n -- pass NULL to have the
+ * library compute exactly that on the device); u_bits = bit
  * length of u (blinding exponents are < u); l = comparison bit length; rand_bits = bit length of the
  * randomizer exponents rho (h^rho table size).                                                        */
 int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_t* g, const uint32_t* h, const uint32_t* g_neg, int kn,

@@ -52,7 +52,12 @@ struct scb_ctx {
 
   // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the previous event
   bool profiling = false;
-  std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
+  std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
+
+  // ticket counters of the dynamically scheduled kernels (GroupIndex::next): a ring of device words, one zeroed per launch
+  unsigned long long* queue_ring = nullptr;
+  int queue_next = 0;
+  unsigned long long* fresh_queue();
 
   int scratch(int which, size_t bytes, void** out);
   int grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block);

@@ -18,6 +18,20 @@ struct GroupIndex {
     return (static_cast<size_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * GPW + (threadIdx.x & 31) / TPI;
   }
   __device__ static __forceinline__ size_t total() { return static_cast<size_t>(gridDim.x) * GROUPS_PER_BLOCK; }
+  // Dynamic work distribution for the long-running kernels: a warp takes the next GPW instances from a global
+  // ticket counter (zeroed by the host before the launch), so no SM idles while another still has a queue
+  // (static round-robin loses up to one whole modexp per group to the ragged last round).  Returns false when
+  // the batch is exhausted; groups of the last warp past the end work on instance B-1 without storing.
+  __device__ static __forceinline__ bool next(unsigned long long* queue, size_t B, size_t& inst, bool& active) {
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(queue, static_cast<unsigned long long>(GPW));
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= B) return false;
+    inst = base + (threadIdx.x & 31) / TPI;
+    active = inst < B;
+    if (!active) inst = B - 1;
+    return true;
+  }
   __device__ static __forceinline__ uint32_t* warp_smem(uint32_t* smem) {
     return smem + (threadIdx.x >> 5) * Geo<L, TPI>::WARP_SMEM_WORDS;
   }
@@ -92,21 +106,19 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp,
          int ewords, size_t exp_stride, int ebits, int wbits, uint32_t* scratch, const uint32_t* __restrict__ mul_in,
-         uint32_t* __restrict__ out, int kout, size_t B) {
+         uint32_t* __restrict__ out, int kout, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   uint32_t* X = scratch + slot * modexp_scratch_words<L, TPI>(wbits);
   uint32_t* ACC = X + K;
   uint32_t* TMP = ACC + K;
   uint32_t* table = TMP + K;
-  const size_t rounds = (B + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t inst = rd * total + slot;
-    const bool active = inst < B;
-    if (!active) inst = B - 1;
+  size_t inst;
+  bool active;
+  while (GI::next(queue, B, inst, active)) {
     load_mont(g, X, TMP, base + inst * kbase, kbase);            // x~ = x*R (reduces double-width bases)
     group_modexp(g, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
     if (mul_in != nullptr) {
@@ -205,18 +217,16 @@ __device__ __forceinline__ void group_fixed_base_mul(const Grp<L, TPI>& g, uint3
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, const uint32_t* __restrict__ exp, int ewords,
-             const uint32_t* __restrict__ mul_in, uint32_t* scratch, uint32_t* __restrict__ out, int k32, size_t B) {
+             const uint32_t* __restrict__ mul_in, uint32_t* scratch, uint32_t* __restrict__ out, int k32, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   uint32_t* ACC = scratch + slot * K;
-  const size_t rounds = (B + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t inst = rd * total + slot;
-    const bool active = inst < B;
-    if (!active) inst = B - 1;
+  size_t inst;
+  bool active;
+  while (GI::next(queue, B, inst, active)) {
     if (mul_in != nullptr) {
       words_to_digits(g, ACC, mul_in + inst * k32, k32);
       mm<L, TPI>(m, g.sm, ACC, ACC, m->r2);

@@ -373,7 +373,8 @@ __device__ __forceinline__ void group_paillier_encode(const Grp<L, TPI>& g, cons
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ plain,
-                   const uint32_t* __restrict__ rho, int ebits, int wbits, uint32_t* scratch, uint32_t* __restrict__ out, size_t M) {
+                   const uint32_t* __restrict__ rho, int ebits, int wbits, uint32_t* scratch, uint32_t* __restrict__ out, size_t M,
+                   unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -384,11 +385,9 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
   uint32_t* ACC = X + K;
   uint32_t* TMP = ACC + K;
   uint32_t* table = TMP + K;
-  const size_t rounds = (M + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t i = rd * total + slot;
-    const bool active = i < M;
-    if (!active) i = M - 1;
+  size_t i;
+  bool active;
+  while (GI::next(queue, M, i, active)) {
     if (rho != nullptr) {
       words_to_digits(g, TMP, rho + i * kN, kN);
       mm<L, TPI>(m, g.sm, X, TMP, m->r2);
@@ -409,7 +408,7 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ y, const uint32_t* xinv,
         const uint32_t* __restrict__ r, const uint32_t* __restrict__ rho, int l, int ebits, int wbits, uint32_t* scratch,
-        uint32_t* __restrict__ out, size_t B) {
+        uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -420,11 +419,9 @@ k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, cons
   uint32_t* ACC = X + K;
   uint32_t* TMP = ACC + K;
   uint32_t* table = TMP + K;
-  const size_t rounds = (B + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t i = rd * total + slot;
-    const bool active = i < B;
-    if (!active) i = B - 1;
+  size_t i;
+  bool active;
+  while (GI::next(queue, B, i, active)) {
     // T = (1 + (2^l + r) N)~ : digits of r plus 2^l (lazy digit, < 2^30)
     words_to_digits(g, TMP, r + i * kN, kN);
     if (g.t == (l / W) / L) TMP[l / W] += 1u << (l % W);
@@ -494,20 +491,18 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_encrypt_bits(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint64_t* __restrict__ beta,
                    const uint8_t* __restrict__ dflag, int l, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew,
-                   uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
+                   uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   const int kn = keys->kn;
   const size_t M = B * (l + 1);
   uint32_t* ACC = scratch + slot * K;
-  const size_t rounds = (M + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t idx = rd * total + slot;
-    const bool active = idx < M;
-    if (!active) idx = M - 1;
+  size_t idx;
+  bool active;
+  while (GI::next(queue, M, idx, active)) {
     const size_t i = idx / (l + 1);
     const int e = static_cast<int>(idx % (l + 1));
     const int bit = (e == 0) ? dflag[i] : static_cast<int>((beta[i] >> (e - 1)) & 1ull);
@@ -579,20 +574,18 @@ __global__ void SCB_GROUP_BOUNDS(L)
 k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* TI, const uint64_t* __restrict__ alpha,
              const uint64_t* __restrict__ alpha_tilde, const uint8_t* __restrict__ delta_a, const uint32_t* __restrict__ r_blind, int rb_words,
              const uint8_t* __restrict__ perm, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew, int l,
-             int ubits, int wbits, int do_blind, uint32_t* scratch, uint32_t* __restrict__ out, size_t B) {
+             int ubits, int wbits, int do_blind, uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
   const size_t slot = GI::slot(), total = GI::total();
   const int kn = keys->kn;
-  const size_t rounds = (B + total - 1) / total;
   const size_t stride = step4_scratch_words<L, TPI>(l, wbits);
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t i = rd * total + slot;
-    const bool active = i < B;
+  size_t i;
+  bool active;
+  while (GI::next(queue, B, i, active)) {
     uint32_t* base = scratch + (active ? i : B + slot) * stride;
-    if (!active) i = B - 1;
     uint32_t* D = base;
     uint32_t* DI = D + K;
     uint32_t* S = D + 2 * K;
@@ -765,7 +758,7 @@ k_crt_decrypt_combine(const ModulusDev* __restrict__ m, const KeysDev* __restric
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ c, const uint32_t* __restrict__ vp,
-              int vp_words, int vp_bits, int wbits, uint32_t* scratch, uint8_t* __restrict__ flags, size_t M) {
+              int vp_words, int vp_bits, int wbits, uint32_t* scratch, uint8_t* __restrict__ flags, size_t M, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -776,11 +769,9 @@ k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ key
   uint32_t* ACC = X + K;
   uint32_t* TMP = ACC + K;
   uint32_t* table = TMP + K;
-  const size_t rounds = (M + total - 1) / total;
-  for (size_t rd = 0; rd < rounds; rd++) {
-    size_t i = rd * total + slot;
-    const bool active = i < M;
-    if (!active) i = M - 1;
+  size_t i;
+  bool active;
+  while (GI::next(queue, M, i, active)) {
     load_mont(g, X, TMP, c + i * kn, kn);                        // (c mod p)~ from the double-width c
     group_modexp(g, ACC, X, vp, vp_words, vp_bits, wbits, table);
     mm<L, TPI>(mp, g.sm, TMP, ACC, mp->unit);

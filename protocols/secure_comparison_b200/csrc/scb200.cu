@@ -103,6 +103,15 @@ int scb_ctx::scratch(int which, size_t bytes, void** out) {
   return SCB_OK;
 }
 
+unsigned long long* scb_ctx::fresh_queue() {
+  constexpr int RING = 64;
+  if (!queue_ring && cudaMalloc(&queue_ring, sizeof(unsigned long long) * RING) != cudaSuccess) return nullptr;
+  unsigned long long* q = queue_ring + queue_next;
+  queue_next = (queue_next + 1) % RING;
+  if (cudaMemsetAsync(q, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
+  return q;
+}
+
 // -------------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------------
@@ -139,6 +148,7 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   if (ctx->secret_dev) cudaFree(ctx->secret_dev);
   if (ctx->vp_dev) cudaFree(ctx->vp_dev);
   if (ctx->crt_exp_dev) cudaFree(ctx->crt_exp_dev);
+  if (ctx->queue_ring) cudaFree(ctx->queue_ring);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -246,9 +256,13 @@ int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, in
   void* scratch = nullptr;
   int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * modexp_scratch_words<L, TPI>(wbits) * sizeof(uint32_t), &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_modexp<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, base, kbase, exp, ewords, estride, ebits, wbits,
-                                                               static_cast<uint32_t*>(scratch), mul_in, out, kout, B);
-  return ctx->launched("k_modexp");
+                                                               static_cast<uint32_t*>(scratch), mul_in, out, kout, B, queue);
+  char label[64];
+  snprintf(label, sizeof(label), "k_modexp<%d,%d>[e=%d]", L, TPI, ebits);   // profile label: geometry and exponent length
+  return ctx->launched(label);
 }
 
 template <int L, int TPI>
@@ -287,8 +301,10 @@ int launch_fixed_base(scb_ctx* ctx, const scb_ctx::Mod& md, const scb_ctx::Fixed
   void* scratch = nullptr;
   int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * G::K * sizeof(uint32_t), &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_fixed_base<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, fb.table, fb.nwin, exp, ewords, mul_in,
-                                                                   static_cast<uint32_t*>(scratch), out, md.k32, B);
+                                                                   static_cast<uint32_t*>(scratch), out, md.k32, B, queue);
   return ctx->launched("k_fixed_base");
 }
 

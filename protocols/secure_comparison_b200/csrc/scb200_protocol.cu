@@ -262,7 +262,7 @@ extern "C" int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, in
 
 extern "C" int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_t* g, const uint32_t* h, const uint32_t* g_neg, int kn,
                                   int u_bits, int l, int rand_bits) {
-  if (!ctx || !n || !g || !h || !g_neg || kn <= 0 || kn > MAXW - 4 || l < 1 || l > MAX_L || u_bits < 2 || u_bits > 96 || rand_bits < 1)
+  if (!ctx || !n || !g || !h || kn <= 0 || kn > MAXW - 4 || l < 1 || l > MAX_L || u_bits < 2 || u_bits > 96 || rand_bits < 1)
     return fail(ctx, SCB_EINVAL, "scb_dgk_set_public: bad argument");
   cudaSetDevice(ctx->device);
   int rc = scb_modulus_load(ctx, SCB_MOD_DGK_N, n, kn);
@@ -277,7 +277,12 @@ extern "C" int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_
   // g~, g_neg~ ; c_sa[s==-1][alpha] = enc(s) * enc(alpha): [0][0] = g, [0][1] = g*g, [1][0] = g_neg, [1][1] = g_neg*g
   std::vector<uint32_t> words(2 * kn), digs(2 * MAXK), prodA(2 * MAXK), prodB(2 * MAXK), prod(2 * MAXK);
   memcpy(words.data(), g, sizeof(uint32_t) * kn);
-  memcpy(words.data() + kn, g_neg, sizeof(uint32_t) * kn);
+  if (g_neg != nullptr) {
+    memcpy(words.data() + kn, g_neg, sizeof(uint32_t) * kn);
+  } else {
+    uint8_t ok = 0;                 // g^-1 mod n with the library's own inverse kernel
+    if ((rc = scb_modinv(ctx, SCB_MOD_DGK_N, g, words.data() + kn, &ok, 1))) return rc;
+  }
   const int K = md.K;
 #define CALL(L, TPI) const_to_mont<L, TPI>(ctx, md, words.data(), kn, 2, 0, digs.data())
   auto run1 = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
@@ -523,8 +528,10 @@ int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32
   void* scratch = nullptr;
   rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * (modexp_scratch_words<L, TPI>(wbits) + C::K), &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_step1<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, y, xinv, r, rho, l, ebits, wbits,
-                                                                 static_cast<uint32_t*>(scratch), out, B);
+                                                                 static_cast<uint32_t*>(scratch), out, B, queue);
   rc = ctx->launched("k_step1");
   if (rc) return rc;
   (void)kN;
@@ -543,8 +550,10 @@ int phase_paillier_encrypt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* 
   void* scratch = nullptr;
   int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * modexp_scratch_words<L, TPI>(wbits), &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_paillier_encrypt<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, plain, rho, ebits, wbits,
-                                                                            static_cast<uint32_t*>(scratch), out, M);
+                                                                            static_cast<uint32_t*>(scratch), out, M, queue);
   return ctx->launched("k_paillier_encrypt");
 }
 
@@ -558,8 +567,10 @@ int phase_dgk_encrypt_bits(scb_ctx* ctx, const uint64_t* beta, const uint8_t* df
   void* scratch = nullptr;
   int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * C::K, &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_dgk_encrypt_bits<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, beta, dflag, l, fb.table, fb.nwin, rho, ew,
-                                                                            static_cast<uint32_t*>(scratch), out, B);
+                                                                            static_cast<uint32_t*>(scratch), out, B, queue);
   return ctx->launched("k_dgk_encrypt_bits");
 }
 
@@ -600,9 +611,11 @@ int phase_step4(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const u
   bool any_fail = false;
   rc = batch_modinv_mont<L, TPI>(ctx, SCB_MOD_DGK_N, Tw, B, TI, ok, &any_fail);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_step4_main<L, TPI><<<gridB, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, TI, alpha, alpha_t, delta_a, r_blind, rb_words, perm,
                                                                        fb.table, fb.nwin, rho, ew, l, ubits, wbits, do_blind,
-                                                                       static_cast<uint32_t*>(s4), out, B);
+                                                                       static_cast<uint32_t*>(s4), out, B, queue);
   if ((rc = ctx->launched("k_step4_main"))) return rc;
   if (any_fail) return fail(ctx, SCB_ENOTINV, "scb_initiator_step4: a DGK ciphertext has no inverse mod n");
   return SCB_OK;
@@ -617,8 +630,10 @@ int phase_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M) {
   void* scratch = nullptr;
   int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * modexp_scratch_words<L, TPI>(wbits), &scratch);
   if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_dgk_is_zero<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, c, ctx->vp_dev, static_cast<int>(ctx->dgk_vp.size()),
-                                                                       ctx->dgk_vp_bits, wbits, static_cast<uint32_t*>(scratch), flags, M);
+                                                                       ctx->dgk_vp_bits, wbits, static_cast<uint32_t*>(scratch), flags, M, queue);
   return ctx->launched("k_dgk_is_zero");
 }
 

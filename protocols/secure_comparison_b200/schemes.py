@@ -64,14 +64,13 @@ def as_limbs(values, k: int) -> np.ndarray:
     return ints_to_limbs([_raw(v) for v in values], k)
 
 
-def _dgk_raw_of_minus_one(dgk) -> int:
+def _dgk_raw_of_minus_one(dgk) -> Optional[int]:
     """The raw ciphertext the scheme itself produces for plaintext -1 without encoding
     (``scheme_dgk.unsafe_encrypt(s, apply_encoding=False)`` with s = -1, reference initiator.py:460).
     Asking the scheme keeps us bit-compatible whatever its negative-exponent convention is."""
-    try:
+    if hasattr(dgk, "unsafe_encrypt"):
         return _raw(dgk.unsafe_encrypt(-1, apply_encoding=False))
-    except Exception:
-        return pow(dgk.public_key.g, -1, dgk.public_key.n)
+    return None      # plain key holders: the engine derives g^-1 mod n on the device (pow_mod's convention, U4)
 
 
 class SchemeEngine(Engine):
@@ -130,10 +129,15 @@ class SchemeEngine(Engine):
         if self.dgk_n != n or self.l != l or self.rand_words != limbs_for_bits(rand_bits):
             kn = limbs_for_bits(n.bit_length())
             g_neg = _dgk_raw_of_minus_one(scheme)
-            n_w, g_w, h_w, gn_w = (int_to_limbs(v, kn) for v in (n, int(pk.g), int(pk.h), g_neg))
+            n_w, g_w, h_w = (int_to_limbs(v, kn) for v in (n, int(pk.g), int(pk.h)))
+            gn_w = None if g_neg is None else int_to_limbs(g_neg, kn)
             self._check(self.lib.scb_dgk_set_public(self.ctx, nat._ptr(n_w), nat._ptr(g_w), nat._ptr(h_w), nat._ptr(gn_w), kn,
                                                     u.bit_length(), l, rand_bits))
             self.dgk_n, self.kn, self.l, self.u = n, kn, l, u
+            self._moduli[nat.MOD_DGK_N] = (n, kn)
+            if g_neg is None:
+                from .limbs import limbs_to_int
+                g_neg = limbs_to_int(self.modinv(nat.MOD_DGK_N, g_w.reshape(1, kn))[0])
             self.dgk_g, self.dgk_g_neg = int(pk.g), g_neg
             self.rand_words = limbs_for_bits(rand_bits)
             self.rb_words = limbs_for_bits(u.bit_length())
