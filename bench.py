@@ -287,26 +287,54 @@ def run_ours(args):
         "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
     }
 
+    # ---- second half of the BASELINE metric: 2048-bit modexp/s (full-length per-element exponents, modulus = DGK n),
+    #      device resident, k_modexp<18,4>, SURVEY 8d unit = 20.56 M MAC per modexp
+    MB = B
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
+    d_mb = torch.randint(-2 ** 31, 2 ** 31 - 1, (MB, kn), dtype=torch.int32, device="cuda", generator=g)
+    d_mb[:, kn - 1] &= 0x3FFFFFFF                                   # < 2^(32 kn - 2) < n
+    d_me = torch.randint(-2 ** 31, 2 ** 31 - 1, (MB, kn), dtype=torch.int32, device="cuda", generator=g)
+    d_mo = torch.empty((MB, kn), **i32)
+    torch.cuda.synchronize()
+
+    def modexp_pass():
+        eng.modexp_dev(nat.MOD_DGK_N, d_mb, d_me, kn, False, 32 * kn, None, d_mo, MB)
+
+    modexp_pass()
+    eng.sync()
+    with torch.cuda.stream(stream):
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        modexp_pass()
+        modexp_pass()
+        m1.record(stream)
+    eng.sync()
+    mx_ms = m0.elapsed_time(m1) / 2
+    if world > 1:
+        t = torch.tensor([mx_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mx_ms = float(t.item())
+    modexp_rate = world * MB / (mx_ms * 1e-3)
+    modexp_2048 = {"value": round(modexp_rate, 1), "unit": "modexp/s", "bits": 32 * kn, "exponent_bits": 32 * kn, "batch_per_gpu": MB,
+                   "ms": round(mx_ms, 3), "frac_of_int_peak": round(modexp_rate / world * 20.56e6 / INT_PEAK_MAC_PER_S, 4)}
+
     # ---- e2e: host buffers through the synchronous C-ABI calls (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         h = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory().numpy() for k, v in w.items()}
         h = {k: (v.view(np.uint32) if v.dtype == np.int32 else v) for k, v in h.items()}
 
-        def step_host():
-            z_enc = eng.initiator_step1(h["x"], h["y"], h["r"], h["rho_z"], l)
-            z = eng.paillier_decrypt(z_enc)
-            db = eng.keyholder_step4ab(z, l, h["rho_db"])
-            c = eng.initiator_step4(db, h["r"], h["delta_a"], h["r_blind"], h["perm"], h["rho_c"], l)
-            delta_b, enc3 = eng.keyholder_step4j_5(c, z, h["rho_enc3"], l)
-            return eng.initiator_step6_7(enc3, h["r"], h["delta_a"], l)
+        # the public host-buffer API: LocalPipeline = the five party-phases through the synchronous host-pointer C-ABI calls,
+        # batch split in chunks over two contexts (streams) so that one chunk's PCIe copies overlap another's kernels
+        from protocols.secure_comparison_b200.pipeline import LocalPipeline
+        pipe = LocalPipeline(paillier, dgk, l, device=local, n_contexts=2, chunks=4)
+        res = pipe.arena.empty((B, kc))
 
-        step_host()
+        pipe.compare(h, res)                      # warm-up: scratch growth, pinned result buffers
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            res = step_host()
-        eng.sync()
+            pipe.compare(h, res)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -318,7 +346,9 @@ def run_ours(args):
         d2h = B * kc * 4 + B * kN * 4 + B * E + B * E + B * (1 + 3 * kc * 4) + B * kc * 4
         same = bool(np.array_equal(res, d_res.cpu().numpy().view(np.uint32)))
         e2e = {"value": round(world * B * args.steps / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same}
+               "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same,
+               "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 4 chunks, pinned buffers)"}
+        pipe.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle as the timed CPU port, never on the product path
     cpu = None
@@ -337,6 +367,7 @@ def run_ours(args):
                        "sharding": "contiguous block of the global batch per rank, no data-path collective"},
             "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "modexp_2048": modexp_2048,
             "modexp_4096_per_s_in_step1_kernel": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
         print(json.dumps(line), flush=True)

@@ -73,6 +73,15 @@ def _dgk_raw_of_minus_one(dgk) -> Optional[int]:
     return None      # plain key holders: the engine derives g^-1 mod n on the device (pow_mod's convention, U4)
 
 
+def _out(out, shape, dtype=np.uint32) -> np.ndarray:
+    """Caller-provided result buffer (e.g. pinned host memory reused across calls) or a fresh array."""
+    if out is None:
+        return np.empty(shape, dtype=dtype)
+    if out.dtype != dtype or tuple(out.shape) != tuple(shape) or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+    return out
+
+
 class SchemeEngine(Engine):
     """One GPU context with a Paillier and a DGK key loaded."""
 
@@ -170,12 +179,12 @@ class SchemeEngine(Engine):
         self._check(self.lib.scb_paillier_encrypt(self.ctx, nat._ptr(plain), nat._ptr(rho_a), nat._ptr(out), M))
         return out
 
-    def paillier_decrypt(self, c: np.ndarray) -> np.ndarray:
+    def paillier_decrypt(self, c: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Raw plaintext in ``[0, N)`` -- ``decrypt(c, apply_encoding=False)``."""
         c = nat._host_u32(c)
         shape = c.shape[:-1]
         M = int(np.prod(shape)) if shape else 1
-        out = np.empty(shape + (self.kN,), dtype=np.uint32)
+        out = _out(out, shape + (self.kN,))
         self._check(self.lib.scb_paillier_decrypt(self.ctx, nat._ptr(c), nat._ptr(out), M))
         return out
 
@@ -188,17 +197,18 @@ class SchemeEngine(Engine):
         return flags
 
     # ------------------------------------------------------------------ fused phases (host buffers)
-    def initiator_step1(self, x: np.ndarray, y: np.ndarray, r: np.ndarray, rho: Optional[np.ndarray], l: int) -> np.ndarray:
+    def initiator_step1(self, x: np.ndarray, y: np.ndarray, r: np.ndarray, rho: Optional[np.ndarray], l: int,
+                        out: Optional[np.ndarray] = None) -> np.ndarray:
         x = nat._host_u32(x)
         B = x.shape[0]
         y = nat._host_u32(y, (B, self.kc))
         r = nat._host_u32(r, (B, self.kN))
         rho_a = None if rho is None else nat._host_u32(rho, (B, self.kN))
-        out = np.empty((B, self.kc), dtype=np.uint32)
+        out = _out(out, (B, self.kc))
         self._check(self.lib.scb_initiator_step1(self.ctx, nat._ptr(x), nat._ptr(y), nat._ptr(r), nat._ptr(rho_a), l, nat._ptr(out), B))
         return out
 
-    def keyholder_step4ab(self, z: np.ndarray, l: int, rho: Optional[np.ndarray]) -> np.ndarray:
+    def keyholder_step4ab(self, z: np.ndarray, l: int, rho: Optional[np.ndarray], out: Optional[np.ndarray] = None) -> np.ndarray:
         z = nat._host_u32(z)
         B = z.shape[0]
         rho_a, rw = None, 0
@@ -207,12 +217,12 @@ class SchemeEngine(Engine):
             if rho_a.shape[:2] != (B, l + 1):
                 raise ValueError("rho must be [B][l+1][words]")
             rw = rho_a.shape[2]
-        out = np.empty((B, l + 1, self.kn), dtype=np.uint32)
+        out = _out(out, (B, l + 1, self.kn))
         self._check(self.lib.scb_keyholder_step4ab(self.ctx, nat._ptr(z), l, nat._ptr(rho_a), rw, nat._ptr(out), B))
         return out
 
     def initiator_step4(self, db_enc: np.ndarray, r: np.ndarray, delta_a: np.ndarray, r_blind: Optional[np.ndarray],
-                        perm: Optional[np.ndarray], rho: Optional[np.ndarray], l: int) -> np.ndarray:
+                        perm: Optional[np.ndarray], rho: Optional[np.ndarray], l: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         db_enc = nat._host_u32(db_enc)
         B = db_enc.shape[0]
         if db_enc.shape != (B, l + 1, self.kn):
@@ -230,18 +240,19 @@ class SchemeEngine(Engine):
         if rho is not None:
             rho_a = nat._host_u32(rho)
             rw = rho_a.shape[2]
-        out = np.empty((B, l + 1, self.kn), dtype=np.uint32)
+        out = _out(out, (B, l + 1, self.kn))
         self._check(self.lib.scb_initiator_step4(self.ctx, nat._ptr(db_enc), nat._ptr(r), nat._ptr(delta_a), nat._ptr(rb), rbw, nat._ptr(pm),
                                                  nat._ptr(rho_a), rw, l, nat._ptr(out), B))
         return out
 
-    def keyholder_step4j_5(self, c: np.ndarray, z: np.ndarray, rho: Optional[np.ndarray], l: int) -> Tuple[np.ndarray, np.ndarray]:
+    def keyholder_step4j_5(self, c: np.ndarray, z: np.ndarray, rho: Optional[np.ndarray], l: int,
+                           out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
         c = nat._host_u32(c)
         B = c.shape[0]
         z = nat._host_u32(z, (B, self.kN))
         rho_a = None if rho is None else nat._host_u32(rho, (B, 3, self.kN))
-        delta_b = np.zeros(B, dtype=np.uint8)
-        enc3 = np.empty((B, 3, self.kc), dtype=np.uint32)
+        delta_b = _out(None if out is None else out[0], (B,), np.uint8)
+        enc3 = _out(None if out is None else out[1], (B, 3, self.kc))
         self._check(self.lib.scb_keyholder_step4j_5(self.ctx, nat._ptr(c), nat._ptr(z), nat._ptr(rho_a), l, nat._ptr(delta_b), nat._ptr(enc3), B))
         return delta_b, enc3
 
@@ -254,12 +265,12 @@ class SchemeEngine(Engine):
         self._check(self.lib.scb_keyholder_step5(self.ctx, nat._ptr(z), nat._ptr(delta_b), nat._ptr(rho_a), l, nat._ptr(enc3), B))
         return enc3
 
-    def initiator_step6_7(self, enc3: np.ndarray, r: np.ndarray, delta_a: np.ndarray, l: int) -> np.ndarray:
+    def initiator_step6_7(self, enc3: np.ndarray, r: np.ndarray, delta_a: np.ndarray, l: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         enc3 = nat._host_u32(enc3)
         B = enc3.shape[0]
         r = nat._host_u32(r, (B, self.kN))
         delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8).reshape(B)
-        out = np.empty((B, self.kc), dtype=np.uint32)
+        out = _out(out, (B, self.kc))
         self._check(self.lib.scb_initiator_step6_7(self.ctx, nat._ptr(enc3), nat._ptr(r), nat._ptr(delta_a), l, nat._ptr(out), B))
         return out
 
