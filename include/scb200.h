@@ -98,7 +98,8 @@ int scb_modmul_dev(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b,
 int scb_modinv(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
 int scb_modinv_dev(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
 
-/* Fixed-base exponentiation with a precomputed 8-bit window table: out[i] = mul_in[i] * base^exp[i].
+/* Fixed-base exponentiation with a precomputed window table (8-bit windows, widened to 16-bit ones when the
+ * table fits: (exp_bits/16) * 65536 residues): out[i] = mul_in[i] * base^exp[i].
  * scb_fixed_base_load builds the table for `base` (k32 words) and exponents of at most exp_bits bits
  * in table slot `tslot` (0..3) over modulus slot `slot`.  This is DGK's randomizer h^rho
  * (keyholder.py:106-108, initiator.py:153-154).                                                      */
@@ -123,7 +124,10 @@ int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, int lambda_wo
  * Implies scb_paillier_set_private (lambda, mu are not needed).  scb_set_option(SCB_OPT_PAILLIER_CRT, 0)
  * switches back to the public formulas (c^lambda mod N^2, rho^N mod N^2) when those were loaded too.     */
 int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t* q, int kP);
-enum { SCB_OPT_PAILLIER_CRT = 1 };
+enum {
+  SCB_OPT_PAILLIER_CRT = 1,     /* KeyHolder Paillier work over p, p^2, q, q^2 (default 1 when the primes are loaded) */
+  SCB_OPT_FIXED_BASE_WIDE = 2   /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
+};
 int scb_set_option(scb_ctx* ctx, int option, int value);
 /* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1
  * (unsafe_encrypt(-1, apply_encoding=False), initiator.py:460; pow_mod gives g^-1 mod n -- pass NULL to have the

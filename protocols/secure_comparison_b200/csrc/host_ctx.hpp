@@ -23,8 +23,13 @@ struct scb_ctx {
     std::vector<uint32_t> words;
   };
   struct FixedBase {
-    uint32_t* table = nullptr;   // [nwin][256][K] Montgomery digits
-    int nwin = 0, slot = -1, exp_bits = 0;
+    uint32_t* table = nullptr;   // [nwin][256][K] Montgomery digits (8-bit windows)
+    uint32_t* table16 = nullptr; // [nwin16][65536][K] (16-bit windows; optional, built from `table`)
+    int nwin = 0, nwin16 = 0, slot = -1, exp_bits = 0;
+    // what the exponentiation kernels use
+    const uint32_t* use_table() const { return table16 ? table16 : table; }
+    int use_nwin() const { return table16 ? nwin16 : nwin; }
+    int use_wbits() const { return table16 ? 16 : 8; }
     bool loaded = false;
   };
 
@@ -47,6 +52,7 @@ struct scb_ctx {
   uint32_t* vp_dev = nullptr;         // v_p words
   // Paillier CRT form: device exponents [e1p, p, p-1, e1q, q, q-1] (kP words each) and their bit lengths
   bool have_paillier_crt = false, use_crt = true;
+  bool fb_wide = true;                // build 16-bit-window fixed-base tables when memory allows
   uint32_t* crt_exp_dev = nullptr;
   int crt_e1_bits[2] = {0, 0}, crt_P_bits[2] = {0, 0};
 

@@ -37,7 +37,7 @@ struct GroupIndex {
   }
 };
 
-// bits [pos, pos+w) of a little-endian word array (w <= 8), zero beyond `words`
+// bits [pos, pos+w) of a little-endian word array (w <= 16), zero beyond `words`
 __device__ __forceinline__ uint32_t get_bits(const uint32_t* __restrict__ e, int words, int pos, int w) {
   const int i = pos >> 5, sh = pos & 31;
   const uint32_t lo = (i < words) ? __ldg(e + i) : 0u;
@@ -203,20 +203,40 @@ __global__ void SCB_GROUP_BOUNDS(L) k_fb_fill(const ModulusDev* __restrict__ m, 
   }
 }
 
-// acc (Montgomery, lazy) *= base^exp using the 8-bit window table.  e: this group's exponent words.
+// step 3 (optional): 16-bit windows from pairs of 8-bit windows, T16[j][v] = T8[2j][v & 255] * T8[2j+1][v >> 8]:
+// nwin16 * 65536 entries (472 MB for DGK-2048's 400-bit randomizer exponents -- HBM capacity is what a B200 has
+// plenty of), one independent product each, so h^rho costs 25 products instead of 50.
+template <int L, int TPI>
+__global__ void SCB_GROUP_BOUNDS(L) k_fb16_fill(const ModulusDev* __restrict__ m, const uint32_t* table8, uint32_t* table16, size_t M,
+                                                uint32_t* dump, unsigned long long* queue) {
+  extern __shared__ uint32_t smem[];
+  using GI = GroupIndex<L, TPI>;
+  constexpr int K = Geo<L, TPI>::K;
+  const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
+  const size_t slot = GI::slot();
+  size_t idx;
+  bool active;
+  while (GI::next(queue, M, idx, active)) {
+    const size_t j = idx >> 16, v = idx & 0xffff;
+    uint32_t* dst = active ? table16 + idx * K : dump + slot * K;
+    mm<L, TPI>(m, g.sm, dst, table8 + ((2 * j) * 256 + (v & 255)) * K, table8 + ((2 * j + 1) * 256 + (v >> 8)) * K);
+  }
+}
+
+// acc (Montgomery, lazy) *= base^exp using the window table (wbits = 8 or 16).  e: this group's exponent words.
 template <int L, int TPI>
 __device__ __forceinline__ void group_fixed_base_mul(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* table, int nwin,
-                                                     const uint32_t* __restrict__ e, int ewords) {
+                                                     const uint32_t* __restrict__ e, int ewords, int wbits = 8) {
   constexpr int K = Geo<L, TPI>::K;
   for (int j = 0; j < nwin; j++) {
-    const uint32_t v = get_bits(e, ewords, j * 8, 8);
-    mm<L, TPI>(g.m, g.sm, acc, acc, table + (static_cast<size_t>(j) * 256 + v) * K);
+    const uint32_t v = get_bits(e, ewords, j * wbits, wbits);
+    mm<L, TPI>(g.m, g.sm, acc, acc, table + ((static_cast<size_t>(j) << wbits) + v) * K);
   }
 }
 
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
-k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, const uint32_t* __restrict__ exp, int ewords,
+k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, int fbw, const uint32_t* __restrict__ exp, int ewords,
              const uint32_t* __restrict__ mul_in, uint32_t* scratch, uint32_t* __restrict__ out, int k32, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
@@ -233,7 +253,7 @@ k_fixed_base(const ModulusDev* __restrict__ m, const uint32_t* table, int nwin, 
     } else {
       copy_digits(g, ACC, m->one);
     }
-    group_fixed_base_mul(g, ACC, table, nwin, exp + inst * ewords, ewords);
+    group_fixed_base_mul(g, ACC, table, nwin, exp + inst * ewords, ewords, fbw);
     mm<L, TPI>(m, g.sm, ACC, ACC, m->unit);
     canonical_store(g, ACC, out + inst * k32, k32, active);
   }

@@ -490,7 +490,7 @@ k_step67(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, con
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_encrypt_bits(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint64_t* __restrict__ beta,
-                   const uint8_t* __restrict__ dflag, int l, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew,
+                   const uint8_t* __restrict__ dflag, int l, const uint32_t* fb_table, int nwin, int fbw, const uint32_t* __restrict__ rho, int ew,
                    uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
@@ -507,7 +507,7 @@ k_dgk_encrypt_bits(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
     const int e = static_cast<int>(idx % (l + 1));
     const int bit = (e == 0) ? dflag[i] : static_cast<int>((beta[i] >> (e - 1)) & 1ull);
     copy_digits(g, ACC, bit ? keys->g_m : m->one);
-    if (rho != nullptr) group_fixed_base_mul(g, ACC, fb_table, nwin, rho + idx * ew, ew);
+    if (rho != nullptr) group_fixed_base_mul(g, ACC, fb_table, nwin, rho + idx * ew, ew, fbw);
     mm<L, TPI>(m, g.sm, ACC, ACC, m->unit);
     canonical_store(g, ACC, out + idx * kn, kn, active);
   }
@@ -573,7 +573,7 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* TI, const uint64_t* __restrict__ alpha,
              const uint64_t* __restrict__ alpha_tilde, const uint8_t* __restrict__ delta_a, const uint32_t* __restrict__ r_blind, int rb_words,
-             const uint8_t* __restrict__ perm, const uint32_t* fb_table, int nwin, const uint32_t* __restrict__ rho, int ew, int l,
+             const uint8_t* __restrict__ perm, const uint32_t* fb_table, int nwin, int fbw, const uint32_t* __restrict__ rho, int ew, int l,
              int ubits, int wbits, int do_blind, uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
@@ -645,7 +645,7 @@ k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys,
       }
       if (rho != nullptr) {
         copy_digits(g, U, res);
-        group_fixed_base_mul(g, U, fb_table, nwin, rho + (i * (l + 1) + k) * ew, ew);
+        group_fixed_base_mul(g, U, fb_table, nwin, rho + (i * (l + 1) + k) * ew, ew, fbw);
         res = U;
       }
       mm<L, TPI>(m, g.sm, S2, res, m->unit);

@@ -140,8 +140,10 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& m : ctx->mod)
     if (m.dev) cudaFree(m.dev);
-  for (auto& t : ctx->fb)
+  for (auto& t : ctx->fb) {
     if (t.table) cudaFree(t.table);
+    if (t.table16) cudaFree(t.table16);
+  }
   for (int i = 0; i < scb_ctx::NSCRATCH; i++)
     if (ctx->scratch_ptr[i]) cudaFree(ctx->scratch_ptr[i]);
   if (ctx->keys_dev) cudaFree(ctx->keys_dev);
@@ -292,6 +294,22 @@ int launch_fb_build(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base_d
 }
 
 template <int L, int TPI>
+int launch_fb16_build(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* table8, uint32_t* table16, int nwin16) {
+  using G = Geo<L, TPI>;
+  const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
+  const size_t M = static_cast<size_t>(nwin16) << 16;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_fb16_fill<L, TPI>), smem, M, gpb);
+  void* dump = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * G::K * sizeof(uint32_t), &dump);
+  if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  k_fb16_fill<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, table8, table16, M, static_cast<uint32_t*>(dump), queue);
+  return ctx->launched("k_fb16_fill");
+}
+
+template <int L, int TPI>
 int launch_fixed_base(scb_ctx* ctx, const scb_ctx::Mod& md, const scb_ctx::FixedBase& fb, const uint32_t* exp, int ewords,
                       const uint32_t* mul_in, uint32_t* out, size_t B) {
   using G = Geo<L, TPI>;
@@ -303,7 +321,7 @@ int launch_fixed_base(scb_ctx* ctx, const scb_ctx::Mod& md, const scb_ctx::Fixed
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_fixed_base<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, fb.table, fb.nwin, exp, ewords, mul_in,
+  k_fixed_base<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, fb.use_table(), fb.use_nwin(), fb.use_wbits(), exp, ewords, mul_in,
                                                                    static_cast<uint32_t*>(scratch), out, md.k32, B, queue);
   return ctx->launched("k_fixed_base");
 }
@@ -466,13 +484,18 @@ extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint
   if (tslot < 0 || tslot >= scb_ctx::NFB || !base || exp_bits <= 0 || exp_bits > 8192) return fail(ctx, SCB_EINVAL, "scb_fixed_base_load: bad argument");
   const scb_ctx::Mod& md = ctx->mod[slot];
   scb_ctx::FixedBase& fb = ctx->fb[tslot];
-  const int nwin = (exp_bits + 7) / 8;
+  const int nwin16 = (exp_bits + 15) / 16;
+  const int nwin = 2 * nwin16;            // an even number of 8-bit windows, so that they pair up into 16-bit ones
   // + a tail of 128 two-slot private areas used by the surplus groups of the build kernels
   const size_t bytes = (static_cast<size_t>(nwin) * 256 + 256) * md.K * sizeof(uint32_t);
+  if (fb.table || fb.table16) cudaStreamSynchronize(ctx->stream);
   if (fb.table) {
-    cudaStreamSynchronize(ctx->stream);
     cudaFree(fb.table);
     fb.table = nullptr;
+  }
+  if (fb.table16) {
+    cudaFree(fb.table16);
+    fb.table16 = nullptr;
   }
   cudaError_t e = cudaMalloc(&fb.table, bytes);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(fixed-base table)");
@@ -491,6 +514,23 @@ extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint
 #undef CALL
   rc = run();
   if (rc) return rc;
+  // 16-bit windows when the table fits comfortably (it is a capacity trade: HBM is 180 GB); otherwise stay with 8-bit
+  fb.nwin16 = nwin16;
+  const size_t bytes16 = (static_cast<size_t>(nwin16) << 16) * md.K * sizeof(uint32_t);
+  if (ctx->fb_wide && exp_bits >= 32 && bytes16 <= (static_cast<size_t>(8) << 30)) {
+    e = cudaMalloc(&fb.table16, bytes16);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fb.table16 = nullptr;
+    } else {
+      uint32_t* t16 = fb.table16;
+#define CALL(L, TPI) launch_fb16_build<L, TPI>(ctx, md, table, t16, nwin16)
+      auto run16 = [&]() -> int { SCB_DISPATCH_K(md.K, CALL) };
+#undef CALL
+      rc = run16();
+      if (rc) return rc;
+    }
+  }
   rc = scb_sync(ctx);
   if (rc) return rc;
   fb.loaded = true;

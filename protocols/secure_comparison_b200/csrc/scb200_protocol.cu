@@ -338,6 +338,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
   if (!ctx) return SCB_EINVAL;
   switch (option) {
     case SCB_OPT_PAILLIER_CRT: ctx->use_crt = value != 0; return SCB_OK;
+    case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }
 }
@@ -569,7 +570,7 @@ int phase_dgk_encrypt_bits(scb_ctx* ctx, const uint64_t* beta, const uint8_t* df
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_dgk_encrypt_bits<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, beta, dflag, l, fb.table, fb.nwin, rho, ew,
+  k_dgk_encrypt_bits<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, beta, dflag, l, fb.use_table(), fb.use_nwin(), fb.use_wbits(), rho, ew,
                                                                             static_cast<uint32_t*>(scratch), out, B, queue);
   return ctx->launched("k_dgk_encrypt_bits");
 }
@@ -614,7 +615,7 @@ int phase_step4(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const u
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_step4_main<L, TPI><<<gridB, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, TI, alpha, alpha_t, delta_a, r_blind, rb_words, perm,
-                                                                       fb.table, fb.nwin, rho, ew, l, ubits, wbits, do_blind,
+                                                                       fb.use_table(), fb.use_nwin(), fb.use_wbits(), rho, ew, l, ubits, wbits, do_blind,
                                                                        static_cast<uint32_t*>(s4), out, B, queue);
   if ((rc = ctx->launched("k_step4_main"))) return rc;
   if (any_fail) return fail(ctx, SCB_ENOTINV, "scb_initiator_step4: a DGK ciphertext has no inverse mod n");

@@ -146,6 +146,10 @@ class Engine:
         self._check(rc)
         return out if raise_on_failure else (out, ok)
 
+    def set_fixed_base_wide(self, enabled: bool) -> None:
+        """16-bit-window fixed-base tables (default) vs 8-bit windows only; applies to tables loaded afterwards."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_FIXED_BASE_WIDE, int(bool(enabled))))
+
     def fixed_base_load(self, tslot: int, slot: int, base: int, exp_bits: int) -> None:
         k = self.k32(slot)
         words = int_to_limbs(base % self.modulus(slot), k)

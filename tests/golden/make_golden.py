@@ -62,6 +62,9 @@ def make(name: str, paillier_bits: int, dgk_bits: int, v_bits: int, l: int, pair
 
 if __name__ == "__main__":
     rng = random.Random(99)
+    only_large = "--only-large" in sys.argv
+    if only_large:
+        sys.argv.append("--large")
     # the reference's own test sizes: Paillier-1024, DGK n=128/v=20, l=16 (test/conftest.py:22-23,65-66)
     make("golden_p1024_d128_l16.json", 1024, 128, 20, 16, draw_inputs(rng, 40, 16), seed=1)
     # README / BASELINE config 1: x=23, y=42, l=16, Paillier-2048, DGK-2048 v=160 (+ boundary pairs)
@@ -69,3 +72,7 @@ if __name__ == "__main__":
          seed=2)
     # a second bit length on small keys (l = 8; u = next_prime(2^10))
     make("golden_p512_d192_l8.json", 512, 192, 24, 8, draw_inputs(rng, 12, 8, include_reference_pairs=False), seed=3)
+    if "--large" in sys.argv:
+        # BASELINE configs[2] and configs[3] key sizes and bit lengths (a few comparisons each: the files stay small)
+        make("golden_p2048_d2048_l32.json", 2048, 2048, 160, 32, [(23, 42), ((1 << 32) - 1, 5), (123456789, 123456789)], seed=4)
+        make("golden_p4096_d3072_l64.json", 4096, 3072, 160, 64, [(23, 42), ((1 << 64) - 1, (1 << 63) + 12345), (1 << 40, 1 << 40)], seed=5)

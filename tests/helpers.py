@@ -6,7 +6,8 @@ from oracle.protocol import Nonces, Transcript
 from oracle.workload import schemes_from_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_FILES = ["golden_p1024_d128_l16.json", "golden_p512_d192_l8.json", "golden_p2048_d2048_l16.json"]
+GOLDEN_FILES = ["golden_p1024_d128_l16.json", "golden_p512_d192_l8.json", "golden_p2048_d2048_l16.json",
+                "golden_p2048_d2048_l32.json", "golden_p4096_d3072_l64.json"]   # the last two: BASELINE configs[2] / configs[3] sizes
 
 
 def unhex(obj):

@@ -86,13 +86,19 @@ def test_modinv(eng, bits):
     assert limbs_to_ints(eng.modinv(SLOT, ints_to_limbs(good, k))) == [pow(v, -1, n) for v in good]
 
 
-@pytest.mark.parametrize("bits,ebits", [(128, 50), (2048, 400), (3072, 400)])
-def test_fixed_base(eng, bits, ebits):
+@pytest.mark.parametrize("wide", [True, False], ids=["w16", "w8"])
+@pytest.mark.parametrize("bits,ebits", [(128, 50), (2048, 400), (3072, 400), (1024, 31)])
+def test_fixed_base(eng, bits, ebits, wide):
+    """8-bit-window tables and the 16-bit-window tables built from them give the same (exact) powers."""
     rng = random.Random(bits + ebits)
     n = rand_modulus(rng, bits)
     k = eng.load_modulus(SLOT, n)
     h = rng.randrange(2, n)
-    eng.fixed_base_load(0, SLOT, h, ebits)
+    eng.set_fixed_base_wide(wide)
+    try:
+        eng.fixed_base_load(0, SLOT, h, ebits)
+    finally:
+        eng.set_fixed_base_wide(True)
     B = 200
     exps = [rng.getrandbits(ebits) for _ in range(B)]
     exps[:3] = [0, 1, (1 << ebits) - 1]

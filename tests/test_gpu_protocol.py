@@ -108,7 +108,8 @@ def test_individual_steps_reproduce_golden_vectors(name):
     assert np.array_equal(Initiator.steps_6_7(np.stack([zeta1, zeta2, delta_b_enc], axis=1), r, delta_a, l, paillier), result)
 
 
-@pytest.mark.parametrize("pbits,dbits,vbits,l,B", [(1024, 128, 20, 16, 700), (512, 192, 24, 8, 300), (2048, 2048, 160, 16, 24)])
+@pytest.mark.parametrize("pbits,dbits,vbits,l,B", [(1024, 128, 20, 16, 700), (512, 192, 24, 8, 300), (2048, 2048, 160, 16, 24),
+                                                 (2048, 2048, 160, 32, 10), (4096, 3072, 160, 64, 4)])
 def test_fused_phases_match_oracle_on_fresh_batches(pbits, dbits, vbits, l, B):
     paillier, dgk = make_schemes(pbits, dbits, vbits, l)
     reset_engines()
