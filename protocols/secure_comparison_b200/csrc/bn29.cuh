@@ -107,28 +107,18 @@ __device__ __forceinline__ void stage_from(const Grp<L, TPI>& g, const uint32_t*
 // alias a and/or b).  Bounds: a*b < 4 n R / 2^18 or so is plenty -- in practice a, b are lazy values
 // (< 2n, or sums of a few of them) with digits <= 2^29 + 4; the result is < 2n with digits <= 2^29.
 // All 32 lanes of the warp must call this together.
+// The row loop of one Montgomery product on register operands: r = a * b * R^-1 mod n (lazy), with
+//   av[L], nv[L] : this lane's digits of a and of the modulus (registers),
+//   b            : ALREADY staged in the group's shared-memory area (digit j at sm_group[j * GPW]) and made visible
+//                  with __syncwarp() by the caller (stage_digits()); the pad row K may hold anything,
+//   r[L]         : this lane's digits of the result (may be the same array as av: it is written after the last row).
+// All 32 lanes of the warp must call this together (full-mask shuffles).
 template <int L, int TPI>
-__device__ __noinline__ void mm(const ModulusDev* __restrict__ m, uint32_t* sm_group, uint32_t* dst, const uint32_t* a,
-                                const uint32_t* b) {
+__device__ __forceinline__ void mm_rows(const uint32_t (&av)[L], const uint32_t (&nv)[L], const uint32_t np, const uint32_t* __restrict__ sm_group,
+                                        uint32_t (&r)[L]) {
   constexpr int GPW = Geo<L, TPI>::GPW;
   const int t = (threadIdx.x & 31) % TPI;
   const bool top = t == TPI - 1;
-  uint32_t av[L], nv[L];
-  {
-    uint32_t bv[L];
-#pragma unroll
-    for (int i = 0; i < L; i++) bv[i] = b[t * L + i];
-#pragma unroll
-    for (int i = 0; i < L; i++) av[i] = a[t * L + i];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < L; i++) sm_group[(t * L + i) * GPW] = bv[i];
-    __syncwarp();
-  }
-#pragma unroll
-  for (int i = 0; i < L; i++) nv[i] = m->n[t * L + i];
-  const uint32_t np = m->np;
-
   uint64_t acc[L];
 #pragma unroll
   for (int i = 0; i < L; i++) acc[i] = 0;
@@ -157,7 +147,6 @@ __device__ __noinline__ void mm(const ModulusDev* __restrict__ m, uint32_t* sm_g
     }
   }
   // after TPI*L rows the renaming is back to the identity: logical column i is acc[i].
-  uint32_t r[L];
   uint64_t c = 0;
 #pragma unroll
   for (int i = 0; i < L; i++) {
@@ -173,6 +162,40 @@ __device__ __noinline__ void mm(const ModulusDev* __restrict__ m, uint32_t* sm_g
   c2 = (c2 >> W) + r[1];
   r[1] = static_cast<uint32_t>(c2) & DMASK;
   r[2] += static_cast<uint32_t>(c2 >> W);        // <= 2^29: stays a legal lazy digit
+}
+
+// Stage this lane's L digits (registers) into the group's shared-memory operand area and make them visible.
+template <int L, int TPI>
+__device__ __forceinline__ void stage_digits(uint32_t* sm_group, const uint32_t (&bv)[L]) {
+  constexpr int GPW = Geo<L, TPI>::GPW;
+  const int t = (threadIdx.x & 31) % TPI;
+  __syncwarp();                                   // every lane is done reading the previous operand
+#pragma unroll
+  for (int i = 0; i < L; i++) sm_group[(t * L + i) * GPW] = bv[i];
+  __syncwarp();
+}
+
+// dst = a * b * R^-1 mod n, lazy.  a, b, dst: K-digit arrays of THIS group in global memory (dst may
+// alias a and/or b).  Bounds: a*b < 4 n R / 2^18 or so is plenty -- in practice a, b are lazy values
+// (< 2n, or sums of a few of them) with digits <= 2^29 + 4; the result is < 2n with digits <= 2^29.
+// All 32 lanes of the warp must call this together.
+template <int L, int TPI>
+__device__ __noinline__ void mm(const ModulusDev* __restrict__ m, uint32_t* sm_group, uint32_t* dst, const uint32_t* a,
+                                const uint32_t* b) {
+  const int t = (threadIdx.x & 31) % TPI;
+  uint32_t av[L], nv[L];
+  {
+    uint32_t bv[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) bv[i] = b[t * L + i];
+#pragma unroll
+    for (int i = 0; i < L; i++) av[i] = a[t * L + i];
+    stage_digits<L, TPI>(sm_group, bv);
+  }
+#pragma unroll
+  for (int i = 0; i < L; i++) nv[i] = m->n[t * L + i];
+  uint32_t r[L];
+  mm_rows<L, TPI>(av, nv, m->np, sm_group, r);
 #pragma unroll
   for (int i = 0; i < L; i++) dst[t * L + i] = r[i];
 }

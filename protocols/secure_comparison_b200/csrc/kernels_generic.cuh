@@ -48,6 +48,14 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* __restrict__ e, int
 // -------------------------------------------------------------------------------------------------
 // Fixed-window Montgomery exponentiation for ONE group: acc = x~^e (Montgomery form, lazy).
 // xm, acc: K-digit slots; table: (1<<wbits) slots.  All in this group's global scratch.
+//
+// The running value and the modulus stay in REGISTERS across the whole exponentiation: a squaring re-stages the
+// value into shared memory (it is its own b operand) and runs the row loop again -- no global-memory round trip,
+// no operand reloads between the ~2,500 products of a 2048-bit exponent.  Only window products read their table
+// entry from global scratch, and the table build stages x~ once for all 2^w - 2 products.  One software loop
+// drives the three phases (table build, squarings, window products) so that the kernel holds a single inlined
+// copy of the row loop; every branch depends on launch-uniform values only (exponent length, window size), the
+// table INDEX is the only per-group quantity.
 // -------------------------------------------------------------------------------------------------
 template <int L, int TPI>
 __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* xm, const uint32_t* __restrict__ e,
@@ -58,24 +66,55 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
     copy_digits(g, acc, g.m->one);
     return;
   }
-  // table[0] = 1~, table[1] = x~, table[v] = table[v-1] * x~
+  const int t = g.t;
+  uint32_t r[L], nv[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) nv[i] = g.m->n[t * L + i];
+  const uint32_t np = g.m->np;
+  // table[0] = 1~, table[1] = x~; r = x~ and x~ staged as the b operand of the table build
   copy_digits(g, table, g.m->one);
-  copy_digits(g, table + K, xm);
-  for (int v = 2; v < (1 << wbits); v++) mm<L, TPI>(g.m, g.sm, table + static_cast<size_t>(v) * K, table + static_cast<size_t>(v - 1) * K, xm);
-  uint32_t win = get_bits(e, ewords, (nwin - 1) * wbits, wbits);
-  const uint32_t* cur = table + static_cast<size_t>(win) * K;   // first squaring reads the table entry directly
-  if (nwin == 1) {
-    copy_digits(g, acc, cur);
-    return;
-  }
-  for (int i = nwin - 2; i >= 0; i--) {
-    for (int s = 0; s < wbits; s++) {
-      mm<L, TPI>(g.m, g.sm, acc, cur, cur);
-      cur = acc;
+#pragma unroll
+  for (int i = 0; i < L; i++) r[i] = xm[t * L + i];
+#pragma unroll
+  for (int i = 0; i < L; i++) table[K + t * L + i] = r[i];
+  stage_digits<L, TPI>(g.sm, r);
+  const int ntab = (1 << wbits) - 2;                     // products of the table build: table[v] = table[v-1] * x~, v = 2..2^w-1
+  const int nmain = (nwin - 1) * (wbits + 1);            // per remaining window: wbits squarings + 1 window product
+#pragma unroll 1
+  for (int step = 0; step < ntab + nmain; step++) {
+    if (step >= ntab) {
+      const int k = step - ntab;
+      const int pos = k % (wbits + 1);
+      if (k == 0) {
+        // the table is complete (each lane wrote, and now reads, only its own digits): start from the top window
+        const uint32_t win = get_bits(e, ewords, (nwin - 1) * wbits, wbits);
+#pragma unroll
+        for (int i = 0; i < L; i++) r[i] = table[static_cast<size_t>(win) * K + t * L + i];
+      }
+      if (pos < wbits) {
+        stage_digits<L, TPI>(g.sm, r);                   // squaring: the value is its own b operand
+      } else {
+        const int wi = nwin - 2 - k / (wbits + 1);
+        const uint32_t win = get_bits(e, ewords, wi * wbits, wbits);
+        uint32_t bv[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) bv[i] = table[static_cast<size_t>(win) * K + t * L + i];
+        stage_digits<L, TPI>(g.sm, bv);
+      }
     }
-    win = get_bits(e, ewords, i * wbits, wbits);
-    mm<L, TPI>(g.m, g.sm, acc, acc, table + static_cast<size_t>(win) * K);
+    mm_rows<L, TPI>(r, nv, np, g.sm, r);
+    if (step < ntab) {
+#pragma unroll
+      for (int i = 0; i < L; i++) table[static_cast<size_t>(step + 2) * K + t * L + i] = r[i];
+    }
   }
+  if (nmain == 0) {                                      // a single window: the result is a table entry
+    const uint32_t win = get_bits(e, ewords, 0, wbits);
+#pragma unroll
+    for (int i = 0; i < L; i++) r[i] = table[static_cast<size_t>(win) * K + t * L + i];
+  }
+#pragma unroll
+  for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
 }
 
 // dst = x~ (Montgomery form, lazy, < 4n) of the value x stored in `kw` words at `words`; x may be up to twice
