@@ -126,7 +126,9 @@ int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, int lambda_wo
 int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t* q, int kP);
 enum {
   SCB_OPT_PAILLIER_CRT = 1,     /* KeyHolder Paillier work over p, p^2, q, q^2 (default 1 when the primes are loaded) */
-  SCB_OPT_FIXED_BASE_WIDE = 2   /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
+  SCB_OPT_FIXED_BASE_WIDE = 2,  /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
+  SCB_OPT_MODEXP_FP64 = 3       /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
+                                   the IMAD one (default 1; results are bit-identical either way) */
 };
 int scb_set_option(scb_ctx* ctx, int option, int value);
 /* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libscb200.so")
 
 OPT_PAILLIER_CRT = 1
 OPT_FIXED_BASE_WIDE = 2
+OPT_MODEXP_FP64 = 3
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 
 MOD_PAILLIER_N2, MOD_PAILLIER_N, MOD_DGK_N, MOD_DGK_P = 0, 1, 2, 3

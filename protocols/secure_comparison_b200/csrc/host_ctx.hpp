@@ -9,6 +9,7 @@
 
 namespace scb {
 struct ModulusDev;
+struct Modulus52Dev;
 struct KeysDev;
 }  // namespace scb
 
@@ -18,7 +19,8 @@ struct scb_ctx {
 
   struct Mod {
     scb::ModulusDev* dev = nullptr;
-    int K = 0, k32 = 0, bits = 0;
+    scb::Modulus52Dev* dev52 = nullptr;   // constants of the FP64 engine (bn52.cuh); K52 = 0 when the size has no FP64 geometry
+    int K = 0, k32 = 0, bits = 0, K52 = 0;
     bool loaded = false;
     std::vector<uint32_t> words;
   };
@@ -52,6 +54,7 @@ struct scb_ctx {
   uint32_t* vp_dev = nullptr;         // v_p words
   // Paillier CRT form: device exponents [e1p, p, p-1, e1q, q, q-1] (kP words each) and their bit lengths
   bool have_paillier_crt = false, use_crt = true;
+  bool use_f64 = true;                // large exponentiations on the FP64 engine (bn52.cuh) instead of the IMAD engine
   bool fb_wide = true;                // build 16-bit-window fixed-base tables when memory allows
   uint32_t* crt_exp_dev = nullptr;
   int crt_e1_bits[2] = {0, 0}, crt_P_bits[2] = {0, 0};
@@ -75,6 +78,9 @@ int fail(scb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what);
 int config_K_for_bits(int bits);
 int modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
+// out = (mul_in *) base^exp with either engine (FP64 when enabled and the modulus has an FP64 geometry)
+int modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, size_t exp_stride, int exp_bits,
+               const uint32_t* mul_in, uint32_t* out, int kout, size_t B);
 // shared-exponent modexp with a base of kbase words (up to twice the modulus width) and kout-word results
 int modexp_dev_ex(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, int exp_bits, uint32_t* out, int kout, size_t B);
 // out[i] = a[i*a_stride..] * b[i*b_stride..] mod n (stride 0 broadcasts an operand); device pointers

@@ -373,8 +373,8 @@ __device__ __forceinline__ void group_paillier_encode(const Grp<L, TPI>& g, cons
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ plain,
-                   const uint32_t* __restrict__ rho, int ebits, int wbits, uint32_t* scratch, uint32_t* __restrict__ out, size_t M,
-                   unsigned long long* queue) {
+                   const uint32_t* __restrict__ rho, const uint32_t* __restrict__ rho_pow, int ebits, int wbits, uint32_t* scratch,
+                   uint32_t* __restrict__ out, size_t M, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -396,6 +396,11 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
       mm<L, TPI>(m, g.sm, ACC, ACC, TMP);
     } else {
       group_paillier_encode(g, keys, ACC, plain + i * kN, kN);
+      if (rho_pow != nullptr) {                       // rho^N already computed (FP64 engine): [M][2kN] words
+        words_to_digits(g, TMP, rho_pow + i * 2 * kN, 2 * kN);
+        mm<L, TPI>(m, g.sm, TMP, TMP, m->r2);
+        mm<L, TPI>(m, g.sm, ACC, ACC, TMP);
+      }
     }
     mm<L, TPI>(m, g.sm, TMP, ACC, m->unit);
     canonical_store(g, TMP, out + i * 2 * kN, 2 * kN, active);
@@ -407,8 +412,8 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ y, const uint32_t* xinv,
-        const uint32_t* __restrict__ r, const uint32_t* __restrict__ rho, int l, int ebits, int wbits, uint32_t* scratch,
-        uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
+        const uint32_t* __restrict__ r, const uint32_t* __restrict__ rho, const uint32_t* __restrict__ rho_pow, int l, int ebits, int wbits,
+        uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -440,6 +445,10 @@ k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, cons
       mm<L, TPI>(m, g.sm, X, TMP, m->r2);
       group_modexp(g, ACC, X, keys->Nw, kN, ebits, wbits, table);
       mm<L, TPI>(m, g.sm, TMP, ACC, Z);
+    } else if (rho_pow != nullptr) {                  // rho^N already computed (FP64 engine): [B][2kN] words
+      words_to_digits(g, X, rho_pow + i * kc, kc);
+      mm<L, TPI>(m, g.sm, X, X, m->r2);
+      mm<L, TPI>(m, g.sm, TMP, TMP, X);
     }
     mm<L, TPI>(m, g.sm, TMP, TMP, m->unit);
     canonical_store(g, TMP, out + i * kc, kc, active);

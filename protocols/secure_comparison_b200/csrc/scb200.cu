@@ -12,6 +12,7 @@
 
 #include "host_ctx.hpp"
 #include "kernels_generic.cuh"
+#include "kernels_f64.cuh"
 
 using namespace scb;
 
@@ -67,6 +68,14 @@ int scb::config_K_for_bits(int bits) {
   for (int K : Ks)
     if (29 * K >= bits + 2) return K;
   return -1;
+}
+
+static int config_K52_for_bits(int bits) {
+  // R = 2^(52K) must exceed 16n; only the L = 10 geometries are instantiated (10x2, 10x4, 10x8, 10x16)
+  static const int Ks[] = {20, 40, 80, 160};
+  for (int K : Ks)
+    if (52 * K >= bits + 4) return K;
+  return 0;
 }
 
 int scb::fail(scb_ctx* ctx, int code, const char* fmt, ...) {
@@ -138,8 +147,10 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& m : ctx->mod)
+  for (auto& m : ctx->mod) {
     if (m.dev) cudaFree(m.dev);
+    if (m.dev52) cudaFree(m.dev52);
+  }
   for (auto& t : ctx->fb) {
     if (t.table) cudaFree(t.table);
     if (t.table16) cudaFree(t.table16);
@@ -230,6 +241,47 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
   md.bits = bits;
   md.words.assign(n, n + k32);
   md.loaded = true;
+  // ---- FP64 engine constants (52-bit digits as doubles): n, n' = -n^-1 mod 2^52, R, R^2, R^3 mod n with R = 2^(52 K52)
+  md.K52 = config_K52_for_bits(bits);
+  if (md.K52 > 0 && 32 * k32 <= 52 * md.K52) {
+    const int K52 = md.K52;
+    std::vector<uint8_t> buf(sizeof(Modulus52Dev), 0);
+    Modulus52Dev* h52 = reinterpret_cast<Modulus52Dev*>(buf.data());
+    h52->K = K52;
+    h52->k32 = k32;
+    uint64_t n64 = n[0] | (k32 > 1 ? static_cast<uint64_t>(n[1]) << 32 : 0ull), inv64 = n64;
+    for (int i = 0; i < 6; i++) inv64 *= 2ull - n64 * inv64;
+    h52->np = static_cast<double>((0ull - inv64) & ((1ull << 52) - 1ull));
+    auto to52 = [&](const Words& x, double* digits) {
+      for (int d = 0; d < K52; d++) {
+        const int bit = d * 52, w = bit >> 5, sh = bit & 31;
+        auto word = [&](int i) -> uint64_t { return static_cast<size_t>(i) < x.size() ? x[i] : 0u; };
+        uint64_t v = (word(w) | (word(w + 1) << 32)) >> sh;
+        if (sh) v |= word(w + 2) << (64 - sh);
+        digits[d] = static_cast<double>(v & ((1ull << 52) - 1ull));
+      }
+    };
+    to52(nw, h52->n);
+    h52->unit[0] = 1.0;
+    Words y(k32 + 1, 0);
+    y[(bits - 1) >> 5] = 1u << ((bits - 1) & 31);
+    int ee = bits - 1;
+    const int targets52[3] = {52 * K52, 104 * K52, 156 * K52};
+    double* dst52[3] = {h52->one, h52->r2, h52->r3};
+    for (int t = 0; t < 3; t++) {
+      for (; ee < targets52[t]; ee++) words_dbl_mod(y, nw);
+      to52(y, dst52[t]);
+    }
+    if (!md.dev52) {
+      cudaError_t ce2 = cudaMalloc(&md.dev52, sizeof(Modulus52Dev));
+      if (ce2 != cudaSuccess) return cuda_fail(ctx, ce2, "cudaMalloc(modulus52)");
+    }
+    cudaError_t ce2 = cudaMemcpyAsync(md.dev52, h52, sizeof(Modulus52Dev), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce2 == cudaSuccess) ce2 = cudaStreamSynchronize(ctx->stream);
+    if (ce2 != cudaSuccess) return cuda_fail(ctx, ce2, "upload modulus52");
+  } else {
+    md.K52 = 0;
+  }
   return SCB_OK;
 }
 
@@ -264,6 +316,26 @@ int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, in
                                                                static_cast<uint32_t*>(scratch), mul_in, out, kout, B, queue);
   char label[64];
   snprintf(label, sizeof(label), "k_modexp<%d,%d>[e=%d]", L, TPI, ebits);   // profile label: geometry and exponent length
+  return ctx->launched(label);
+}
+
+template <int L, int TPI>
+int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, int kbase, const uint32_t* exp, int ewords, size_t estride, int ebits,
+                    const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
+  using G = Geo52<L, TPI>;
+  const int wbits = window_bits_for(ebits);
+  const size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_modexp52<L, TPI>), smem, B, gpb);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * modexp52_scratch_doubles<L, TPI>(wbits) * sizeof(double), &scratch);
+  if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  k_modexp52<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev52, base, kbase, exp, ewords, estride, ebits, wbits,
+                                                                 static_cast<double*>(scratch), mul_in, out, kout, B, queue);
+  char label[64];
+  snprintf(label, sizeof(label), "k_modexp52<%d,%d>[e=%d]", L, TPI, ebits);
   return ctx->launched(label);
 }
 
@@ -423,6 +495,26 @@ static int check_mod(scb_ctx* ctx, int slot, const char* who) {
   return SCB_OK;
 }
 
+int scb::modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, size_t estride, int exp_bits,
+                    const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
+  const scb_ctx::Mod& md = ctx->mod[slot];
+  if (kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp: output narrower than the modulus");
+  // FP64 engine for real exponentiations (it has no advantage for the few-bit exponents of the DGK blinding)
+  if (ctx->use_f64 && md.K52 > 0 && exp_bits >= 64 && 32 * kbase <= 104 * md.K52) {
+    switch (md.K52) {
+      case 20: return launch_modexp52<10, 2>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 40: return launch_modexp52<10, 4>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 80: return launch_modexp52<10, 8>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 160: return launch_modexp52<10, 16>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      default: break;
+    }
+  }
+  if (32 * kbase > 2 * W * md.K) return fail(ctx, SCB_EINVAL, "modexp: base wider than twice the modulus");
+#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B)
+  SCB_DISPATCH_K(md.K, CALL)
+#undef CALL
+}
+
 extern "C" int scb_modexp_dev(scb_ctx* ctx, int slot, const uint32_t* base, const uint32_t* exp, int exp_words, int exp_shared,
                               int exp_bits, const uint32_t* mul_in, uint32_t* out, size_t B) {
   int rc = check_mod(ctx, slot, "scb_modexp");
@@ -431,19 +523,13 @@ extern "C" int scb_modexp_dev(scb_ctx* ctx, int slot, const uint32_t* base, cons
   if (!base || !exp || !out || exp_words <= 0 || exp_bits < 0 || exp_bits > exp_words * 32) return fail(ctx, SCB_EINVAL, "scb_modexp: bad argument");
   const scb_ctx::Mod& md = ctx->mod[slot];
   const size_t estride = exp_shared ? 0 : static_cast<size_t>(exp_words);
-#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, md.k32, exp, exp_words, estride, exp_bits, mul_in, out, md.k32, B)
-  SCB_DISPATCH_K(md.K, CALL)
-#undef CALL
+  return modexp_any(ctx, slot, base, md.k32, exp, exp_words, estride, exp_bits, mul_in, out, md.k32, B);
 }
 
 // base: [B][kbase] words (kbase up to twice the modulus width: reduced on load); out: [B][kout] words
 int scb::modexp_dev_ex(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, int exp_bits,
                        uint32_t* out, int kout, size_t B) {
-  const scb_ctx::Mod& md = ctx->mod[slot];
-  if (32 * kbase > 2 * W * md.K || kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp_dev_ex: operand width out of range");
-#define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, kbase, exp, exp_words, 0, exp_bits, nullptr, out, kout, B)
-  SCB_DISPATCH_K(md.K, CALL)
-#undef CALL
+  return modexp_any(ctx, slot, base, kbase, exp, exp_words, 0, exp_bits, nullptr, out, kout, B);
 }
 
 extern "C" int scb_modmul_dev(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B) {

@@ -2,6 +2,7 @@
 #include "../../../include/scb200.h"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstring>
 #include <vector>
 
@@ -87,6 +88,11 @@ int upload_keys(scb_ctx* ctx) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "upload keys");
   return SCB_OK;
+}
+
+// device address of the Paillier modulus N (kN words) inside the uploaded key block: the public exponent of rho^N
+const uint32_t* keys_N_words(scb_ctx* ctx) {
+  return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ctx->keys_dev) + offsetof(KeysDev, Nw));
 }
 
 KeysDev* host_keys(scb_ctx* ctx) {
@@ -338,6 +344,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
   if (!ctx) return SCB_EINVAL;
   switch (option) {
     case SCB_OPT_PAILLIER_CRT: ctx->use_crt = value != 0; return SCB_OK;
+    case SCB_OPT_MODEXP_FP64: ctx->use_f64 = value != 0; return SCB_OK;
     case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }
@@ -524,6 +531,18 @@ int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32
   if (rc) return rc;
   const int ebits = md.bits > 0 ? ctx->mod[SCB_MOD_PAILLIER_N].bits : 0;
   const int wbits = window_bits_for(ebits);
+  // the randomizer rho^N mod N^2 on the FP64 engine when it is enabled: a separate launch, then k_step1 only multiplies
+  const uint32_t* rho_pow = nullptr;
+  if (rho != nullptr && ctx->use_f64 && md.K52 > 0) {
+    Arena rp;
+    rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * B * 2 * kN), &rp);
+    if (rc) return rc;
+    uint32_t* pw = rp.take<uint32_t>(B * 2 * kN);
+    rc = scb::modexp_any(ctx, SCB_MOD_PAILLIER_N2, rho, kN, keys_N_words(ctx), kN, 0, ebits, nullptr, pw, 2 * kN, B);
+    if (rc) return rc;
+    rho_pow = pw;
+    rho = nullptr;
+  }
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_step1<L, TPI>), C::SMEM, B, C::GPB);
   const size_t groups = static_cast<size_t>(grid) * C::GPB;
   void* scratch = nullptr;
@@ -531,7 +550,7 @@ int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_step1<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, y, xinv, r, rho, l, ebits, wbits,
+  k_step1<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, y, xinv, r, rho, rho_pow, l, ebits, wbits,
                                                                  static_cast<uint32_t*>(scratch), out, B, queue);
   rc = ctx->launched("k_step1");
   if (rc) return rc;
@@ -546,6 +565,18 @@ int phase_paillier_encrypt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* 
   const scb_ctx::Mod& md = ctx->mod[SCB_MOD_PAILLIER_N2];
   const int ebits = ctx->mod[SCB_MOD_PAILLIER_N].bits;
   const int wbits = window_bits_for(ebits);
+  const uint32_t* rho_pow = nullptr;
+  if (rho != nullptr && ctx->use_f64 && md.K52 > 0) {
+    const int kN = host_keys(ctx)->kN;
+    Arena rp;
+    int rc2 = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * M * 2 * kN), &rp);
+    if (rc2) return rc2;
+    uint32_t* pw = rp.take<uint32_t>(M * 2 * kN);
+    rc2 = scb::modexp_any(ctx, SCB_MOD_PAILLIER_N2, rho, kN, keys_N_words(ctx), kN, 0, ebits, nullptr, pw, 2 * kN, M);
+    if (rc2) return rc2;
+    rho_pow = pw;
+    rho = nullptr;
+  }
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_paillier_encrypt<L, TPI>), C::SMEM, M, C::GPB);
   const size_t groups = static_cast<size_t>(grid) * C::GPB;
   void* scratch = nullptr;
@@ -553,7 +584,7 @@ int phase_paillier_encrypt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* 
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_paillier_encrypt<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, plain, rho, ebits, wbits,
+  k_paillier_encrypt<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, plain, rho, rho_pow, ebits, wbits,
                                                                             static_cast<uint32_t*>(scratch), out, M, queue);
   return ctx->launched("k_paillier_encrypt");
 }

@@ -146,6 +146,10 @@ class Engine:
         self._check(rc)
         return out if raise_on_failure else (out, ok)
 
+    def set_modexp_fp64(self, enabled: bool) -> None:
+        """Large exponentiations on the FP64-pipe multiplier (default) or on the IMAD one; bit-identical results."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_MODEXP_FP64, int(bool(enabled))))
+
     def set_fixed_base_wide(self, enabled: bool) -> None:
         """16-bit-window fixed-base tables (default) vs 8-bit windows only; applies to tables loaded afterwards."""
         self._check(self.lib.scb_set_option(self.ctx, nat.OPT_FIXED_BASE_WIDE, int(bool(enabled))))

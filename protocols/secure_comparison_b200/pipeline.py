@@ -94,12 +94,16 @@ class LocalPipeline:
         if result is None:
             result = np.empty((B, eng0.kc), dtype=np.uint32)
         n = min(self.chunks, max(B, 1))
-        futures = []
-        for j in range(n):
-            lo, hi = shard_range(B, j, n)
-            if hi > lo:
-                slot = j % len(self.engines)
-                futures.append(self.pool.submit(self._run_chunk, j, self.engines[slot], w, lo, hi, result))
+        ranges = [shard_range(B, j, n) for j in range(n)]
+
+        def worker(slot: int) -> None:
+            # a context is not re-entrant: each worker thread owns one engine and walks its own chunks in order
+            for j in range(slot, n, len(self.engines)):
+                lo, hi = ranges[j]
+                if hi > lo:
+                    self._run_chunk(j, self.engines[slot], w, lo, hi, result)
+
+        futures = [self.pool.submit(worker, slot) for slot in range(len(self.engines))]
         for f in futures:
             f.result()
         return result

@@ -26,12 +26,22 @@ def rand_modulus(rng, bits):
 
 # (modulus bits, exponent bits, batch) -- every (L, TPI) kernel configuration is covered:
 # K=36 (<=1042 bits), 54, 72, 108, 144, 216, 288
-SIZES = [(64, 64, 40), (128, 160, 70), (1024, 160, 300), (1536, 160, 150), (2048, 400, 300), (2048, 2048, 130),
-         (3072, 400, 100), (4096, 2048, 70), (6144, 64, 40), (8192, 96, 40)]
+SIZES = [(64, 64, 40), (128, 160, 70), (1024, 160, 300), (1024, 1024, 200), (1536, 160, 150), (2048, 400, 300), (2048, 2048, 130),
+         (3072, 400, 100), (4096, 2048, 70), (6144, 64, 40), (8192, 96, 40), (1000, 70, 64), (2040, 333, 64), (4090, 100, 33)]
 
 
+@pytest.mark.parametrize("fp64", [True, False], ids=["fp64", "imad"])
 @pytest.mark.parametrize("bits,ebits,B", SIZES)
-def test_modexp_matches_pow(eng, bits, ebits, B):
+def test_modexp_matches_pow(eng, bits, ebits, B, fp64):
+    """Both multiplier engines (FP64-pipe 52-bit digits, IMAD 29-bit digits) against Python's pow."""
+    eng.set_modexp_fp64(fp64)
+    try:
+        _modexp_matches_pow(eng, bits, ebits, B)
+    finally:
+        eng.set_modexp_fp64(True)
+
+
+def _modexp_matches_pow(eng, bits, ebits, B):
     rng = random.Random(bits * 7 + ebits)
     n = rand_modulus(rng, bits)
     k = eng.load_modulus(SLOT, n)

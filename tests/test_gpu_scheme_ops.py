@@ -63,12 +63,15 @@ def test_paillier_crt_and_public_formulas_agree(setup):
     want_dec = [oracle.paillier_decrypt_raw(v) for v in c]
     try:
         for crt in (True, False):
-            eng.set_paillier_crt(crt)
-            got = eng.paillier_encrypt(ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN))
-            assert limbs_to_ints(got) == want, f"encrypt+randomize, crt={crt}"
-            assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want_dec, f"decrypt, crt={crt}"
+            for fp64 in (True, False):
+                eng.set_paillier_crt(crt)
+                eng.set_modexp_fp64(fp64)
+                got = eng.paillier_encrypt(ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN))
+                assert limbs_to_ints(got) == want, f"encrypt+randomize, crt={crt}, fp64={fp64}"
+                assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want_dec, f"decrypt, crt={crt}, fp64={fp64}"
     finally:
         eng.set_paillier_crt(True)
+        eng.set_modexp_fp64(True)
 
 
 def test_step1_pieces(setup):
