@@ -261,28 +261,39 @@ def run_ours(args):
     kernels = eng.profile_end()
     step_ms_prof = sum(k["ms"] for k in kernels.values())
     top_name = max(kernels, key=lambda k: kernels[k]["ms"])
-    k1 = kernels.get("k_step1", {"ms": 0.0, "launches": 1})
+    # the B modexps rho^N mod N^2 of Initiator.step_1 + randomize: one launch of k_modexp52<10,8> (FP64 engine, default) or,
+    # with the IMAD engine, the modexp fused inside k_step1<18,8>
+    fp64_engine = "k_modexp52<10,8>[e=2048]" in kernels
+    k1_name = "k_modexp52<10,8>[e=2048]" if fp64_engine else "k_step1"
+    k1 = kernels.get(k1_name, {"ms": 0.0, "launches": 1})
     k1_ms = k1["ms"] / max(k1["launches"], 1)
-    k1_mac = B * MAC_PER_MODEXP_4096_2048                 # algorithmic: B randomizers rho^N mod N^2 (+ 5 products, negligible)
+    k1_mac = B * MAC_PER_MODEXP_4096_2048                 # algorithmic: B randomizers rho^N mod N^2
     achieved = k1_mac / (k1_ms * 1e-3) / 1e12 if k1_ms else 0.0
-    bytes_per_launch = B * (2 * kc * 4 + 2 * kN * 4 + kc * 4)   # x, y, r, rho in; z_enc out (algorithmic HBM bytes)
+    bytes_per_launch = B * (kN * 4 + kc * 4) if fp64_engine else B * (2 * kc * 4 + 2 * kN * 4 + kc * 4)
+    fp64_ops = B * 2458 * (2 * 80 * 80 * 3 + 80 * 4)        # DFMA/DADD thread-instructions of one launch (2,458 products of 80 digits)
     roofline = {
-        "bound": "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy; not hbm, not tensor)",
-        "kernel": "k_step1<18,8>", "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
+        "bound": "multiplier pipes, not hbm and not tensor: " + (
+            "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; dispatch-limited: an FP64 instruction takes two issue slots)"
+            if fp64_engine else "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy)"),
+        "kernel": k1_name if fp64_engine else "k_step1<18,8>", "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
         "kernel_ms_per_launch": round(k1_ms, 3),
         "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic)",
         "frac": round(achieved * 1e12 / INT_PEAK_MAC_PER_S, 4),
-        "peak_source": "hardware rate seen by ncu (IMAD.WIDE.U32: 32 lanes/clk/SM x 148 SMs x 1.965 GHz); the IMAD microbenchmark "
-                       "on this pool sustains 8.6 TMAC/s (profiles/r01_imad_microbench2.jsonl)",
+        "peak_source": "integer-multiply roofline of the north star: IMAD.WIDE.U32 = 32 lanes/clk/SM x 148 SMs x 1.965 GHz (what ncu's fmaheavy "
+                       "pct_of_peak refers to; the IMAD microbenchmark on this pool sustains 8.6 TMAC/s, profiles/r01_imad_microbench2.jsonl)",
         "frac_of_measured_microbench_peak": round(achieved * 1e12 / INT_PEAK_MEASURED_MAC_PER_S, 4),
+        "fp64_pipe_frac": round(fp64_ops / (k1_ms * 1e-3) / (148 * 64 * 1.965e9), 4) if (fp64_engine and k1_ms) else None,
+        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 55 %, "
+                          "issue slots 59 % + one extra dispatch cycle per FP64 instruction (profiles/r01m_ncu_k_modexp52.txt)",
+        "imad_engine_reference": "same launch on the IMAD engine: 833 ms at B=65536 = 6.45 TMAC/s algorithmic, fmaheavy pipe 84-87 % busy (profiles/r01e_ncu_k_step1.txt)",
         "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
-        "traffic_note": "dram bytes of one k_step1 launch scaled from the ncu capture at B=32768 (window tables of 9,472 resident groups "
-                        "exceed L2); ~12 GB/s, non-binding next to hbm_gbs",
+        "traffic_note": "dram bytes per launch scaled from an ncu capture (window tables of the ~9,500 resident groups exceed L2): "
+                        "tens of GB/s, non-binding next to hbm_gbs = 6,550",
         "algorithmic_bytes": int(bytes_per_launch),
         "hbm_gbs_algorithmic": round(bytes_per_launch / (k1_ms * 1e-3) / 1e9, 2) if k1_ms else None,
         "whole_step_frac": round(value / world * MAC_PER_COMPARISON_L16 / INT_PEAK_MAC_PER_S, 4),
-        "whole_step_note": "whole_step_frac counts the reference-faithful 567 M MAC per comparison; CRT on the KeyHolder side and the fixed-base "
-                           "table for h^rho do fewer (identical outputs), so it may exceed the per-kernel fraction",
+        "whole_step_note": "whole_step_frac counts the reference-faithful 567 M MAC per comparison against the INTEGER roofline; it exceeds 1 because the "
+                           "KeyHolder's CRT and the fixed-base tables do fewer multiply-adds for identical outputs and because the exponentiations run on the FP64 pipe",
         "top_kernel_by_time": top_name,
         "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -360,7 +371,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (29-bit digits, 64-bit accumulators)",
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: 52-bit digits in f64 (exponentiations) + 29-bit digits in u32/u64 (everything else)",
             "data": "synthetic (seeded keys, inputs and host-supplied nonces)",
             "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-2048/DGK-2048 (v=160), interactive flow (all randomize() calls)",
                        "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l,
@@ -368,7 +379,7 @@ def run_ours(args):
             "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "modexp_2048": modexp_2048,
-            "modexp_4096_per_s_in_step1_kernel": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
+            "modexp_4096_per_s": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
