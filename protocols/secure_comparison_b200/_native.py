@@ -85,11 +85,14 @@ def declared_symbols():
     return sorted(_SIGNATURES)
 
 
-def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
-    """Load libscb200.so and bind every declared entry point (no GPU needed for this)."""
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load libscb200.so and bind every declared entry point (no GPU needed for this).  ``SCB200_LIB`` selects another
+    build of the same library (kernel-tuning experiments)."""
     global _lib
     if _lib is not None:
         return _lib
+    if path is None:
+        path = os.environ.get("SCB200_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise NativeLibraryError(
             f"{path} is missing: build it with `python -m protocols.secure_comparison_b200.build` "

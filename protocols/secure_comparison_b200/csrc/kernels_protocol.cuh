@@ -761,6 +761,17 @@ k_crt_decrypt_combine(const ModulusDev* __restrict__ m, const KeysDev* __restric
   }
 }
 
+// flags[i] = (x[i] == 1) for k-word values (one thread per value): the comparison half of is_zero when the
+// exponentiation c^{v_p} mod p ran on the FP64 engine
+static __global__ void k_flag_is_one(const uint32_t* __restrict__ x, int k, uint8_t* __restrict__ flags, size_t M) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const uint32_t* xi = x + i * k;
+  bool one = xi[0] == 1u;
+  for (int j = 1; j < k && one; j++) one = xi[j] == 0u;
+  flags[i] = one ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // DGK is_zero: flag = (c^{v_p} mod p == 1)   (keyholder.py:249 -> dgk.is_zero)
 // ------------------------------------------------------------------------------------------------

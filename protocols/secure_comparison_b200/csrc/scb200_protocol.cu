@@ -860,7 +860,20 @@ extern "C" int scb_dgk_is_zero_dev(scb_ctx* ctx, const uint32_t* c, uint8_t* fla
   if (rc) return rc;
   if (M == 0) return SCB_OK;
   if (!c || !flags) return fail(ctx, SCB_EINVAL, "scb_dgk_is_zero: null pointer");
-  const int K = ctx->mod[SCB_MOD_DGK_P].K;
+  const scb_ctx::Mod& mdp = ctx->mod[SCB_MOD_DGK_P];
+  if (ctx->use_f64 && mdp.K52 > 0 && ctx->dgk_vp_bits >= 64) {
+    // c^{v_p} mod p on the FP64 engine (c is reduced mod p on load), then one compare per value
+    const int kn = host_keys(ctx)->kn, kp = mdp.k32;
+    Arena pw;
+    rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * M * kp), &pw);
+    if (rc) return rc;
+    uint32_t* y = pw.take<uint32_t>(M * kp);
+    rc = scb::modexp_any(ctx, SCB_MOD_DGK_P, c, kn, ctx->vp_dev, static_cast<int>(ctx->dgk_vp.size()), 0, ctx->dgk_vp_bits, nullptr, y, kp, M);
+    if (rc) return rc;
+    k_flag_is_one<<<static_cast<unsigned>((M + 127) / 128), 128, 0, ctx->stream>>>(y, kp, flags, M);
+    return ctx->launched("k_flag_is_one");
+  }
+  const int K = mdp.K;
 #define CALL(L, TPI) phase_is_zero<L, TPI>(ctx, c, flags, M)
   SCB_DISPATCH_K(K, CALL)
 #undef CALL
