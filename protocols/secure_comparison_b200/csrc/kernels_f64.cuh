@@ -156,11 +156,10 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
 }
 
 // out[i] = (mul_in[i] *) base[i]^exp[i] mod n
-#ifndef SCB_F64_MIN_BLOCKS
-#define SCB_F64_MIN_BLOCKS 3   // 168 registers: no spills; measured 3 % faster than 4 blocks (128 registers, a few spills)
-#endif
+// registers: L = 10 needs ~150 (3 blocks of 128 threads per SM: measured 3 % faster than 4 blocks with a few spills),
+// L = 15 needs ~230 (2 blocks per SM)
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS, SCB_F64_MIN_BLOCKS)
+__global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 3 : 2))
 k_modexp52(const Modulus52Dev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp, int ewords,
            size_t exp_stride, int ebits, int wbits, double* scratch, const uint32_t* __restrict__ mul_in, uint32_t* __restrict__ out, int kout,
            size_t B, unsigned long long* queue) {

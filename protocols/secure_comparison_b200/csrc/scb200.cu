@@ -71,8 +71,8 @@ int scb::config_K_for_bits(int bits) {
 }
 
 static int config_K52_for_bits(int bits) {
-  // R = 2^(52K) must exceed 16n; only the L = 10 geometries are instantiated (10x2, 10x4, 10x8, 10x16)
-  static const int Ks[] = {20, 40, 80, 160};
+  // R = 2^(52K) must exceed 16n; geometries L x TPI: 10x2, 15x2, 10x4, 15x4, 10x8, 15x8, 10x16
+  static const int Ks[] = {20, 30, 40, 60, 80, 120, 160};
   for (int K : Ks)
     if (52 * K >= bits + 4) return K;
   return 0;
@@ -503,7 +503,10 @@ int scb::modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, con
   if (ctx->use_f64 && md.K52 > 0 && exp_bits >= 64 && 32 * kbase <= 104 * md.K52) {
     switch (md.K52) {
       case 20: return launch_modexp52<10, 2>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 30: return launch_modexp52<15, 2>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
       case 40: return launch_modexp52<10, 4>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 60: return launch_modexp52<15, 4>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 120: return launch_modexp52<15, 8>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
       case 80: return launch_modexp52<10, 8>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
       case 160: return launch_modexp52<10, 16>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
       default: break;
