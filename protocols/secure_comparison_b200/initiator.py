@@ -45,7 +45,9 @@ class Initiator:
     """Player Alice in the secure comparison protocol, initiates."""
 
     def __init__(self, l_maximum_bit_length: int, communicator: Optional[Communicator] = None, other_party: str = "",
-                 scheme_paillier: Any = None, scheme_dgk: Any = None, session_id: int = 0) -> None:
+                 scheme_paillier: Any = None, scheme_dgk: Any = None, session_id: int = 0, *, wire_format: bool = False) -> None:
+        # wire_format (new, keyword-only): exchange each protocol message as one packed blob (wire.py) instead of a numpy array
+        self.wire_format = wire_format
         self.l_maximum_bit_length = l_maximum_bit_length
         self.communicator = communicator
         self.other_party = other_party
@@ -86,13 +88,16 @@ class Initiator:
         rho_z = nonces.get("rho_z")
         if rho_z is None:
             rho_z = random_below(N, B, eng.kN, minimum=1)
+        from . import wire
+        out = (lambda a, kind: wire.pack(a, kind)) if self.wire_format else (lambda a, kind: a)
+        inp = (lambda m, kind: wire.unpack(m, kind) if isinstance(m, (bytes, bytearray, memoryview)) else m)
         z_enc = eng.initiator_step1(x_enc, y_enc, r, rho_z, l)                      # step 1 + randomize
-        await self.communicator.send(self.other_party, z_enc, msg_id=f"step_1_session_{session_id}")
-        db_enc = await self.communicator.recv(self.other_party, msg_id=f"step_4b_session_{session_id}")
+        await self.communicator.send(self.other_party, out(z_enc, wire.KIND_PAILLIER_CT), msg_id=f"step_1_session_{session_id}")
+        db_enc = inp(await self.communicator.recv(self.other_party, msg_id=f"step_4b_session_{session_id}"), wire.KIND_DGK_VECTOR)
         c_is_enc = self.steps_4c_to_4i(db_enc, r, l, self.scheme_dgk, self.scheme_paillier, delta_a=nonces.get("delta_a"),
                                        r_blind=nonces.get("r_blind"), perm=nonces.get("perm"), rho=nonces.get("rho_c"), randomize=True)
-        await self.communicator.send(self.other_party, c_is_enc, msg_id=f"step_4i_session_{session_id}")
-        enc3 = await self.communicator.recv(self.other_party, msg_id=f"step_5_session_{session_id}")
+        await self.communicator.send(self.other_party, out(c_is_enc, wire.KIND_DGK_VECTOR), msg_id=f"step_4i_session_{session_id}")
+        enc3 = inp(await self.communicator.recv(self.other_party, msg_id=f"step_5_session_{session_id}"), wire.KIND_PAILLIER_TRIPLE)
         return eng.initiator_step6_7(enc3, r, self._last_delta_a, l)               # steps 6 + 7
 
     async def receive_encryption_schemes(self, session_id: int = 1) -> None:
@@ -100,14 +105,21 @@ class Initiator:
         (initiator.py:177-203, including its ValueErrors)."""
         if self.communicator is None:
             raise ValueError("Communicator not properly initialized.")
-        received_paillier, received_dgk = await self.communicator.recv(self.other_party, msg_id=f"schemes_session_{session_id}")
+        message = await self.communicator.recv(self.other_party, msg_id=f"schemes_session_{session_id}")
+        if isinstance(message, (bytes, bytearray, memoryview)):
+            from . import wire
+            received_paillier, received_dgk = wire.unpack_schemes(bytes(message))
+            differs = lambda mine, got: not wire.same_public_keys(mine, got)  # noqa: E731  (public parts travel, public parts compare)
+        else:
+            received_paillier, received_dgk = message
+            differs = lambda mine, got: mine != got  # noqa: E731  (the reference's scheme equality)
         if self._scheme_paillier is None:
             self._scheme_paillier = received_paillier
-        elif self.scheme_paillier != received_paillier:
+        elif differs(self.scheme_paillier, received_paillier):
             raise ValueError("Readily available Paillier scheme and received Paillier scheme are different.")
         if self._scheme_dgk is None:
             self._scheme_dgk = received_dgk
-        elif self.scheme_dgk != received_dgk:
+        elif differs(self.scheme_dgk, received_dgk):
             raise ValueError("Readily available DGK scheme and received DGK scheme are different.")
 
     # ------------------------------------------------------------------ steps (static, as in the reference)

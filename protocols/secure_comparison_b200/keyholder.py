@@ -20,7 +20,8 @@ class KeyHolder:
     """Player Bob in the secure comparison protocol, holds the keys."""
 
     def __init__(self, l_maximum_bit_length: int, communicator: Optional[Communicator] = None, other_party: str = "",
-                 scheme_paillier: Any = None, scheme_dgk: Any = None, session_id: int = 0) -> None:
+                 scheme_paillier: Any = None, scheme_dgk: Any = None, session_id: int = 0, *, wire_format: bool = False) -> None:
+        self.wire_format = wire_format      # new, keyword-only: one packed blob per protocol message (wire.py)
         self.l_maximum_bit_length = l_maximum_bit_length
         self.communicator = communicator
         self.other_party = other_party
@@ -49,13 +50,16 @@ class KeyHolder:
         await self.make_and_send_encryption_schemes(session_id)
         l = self.l_maximum_bit_length
         nonces = nonces or {}
-        z_enc = await self.communicator.recv(self.other_party, msg_id=f"step_1_session_{session_id}")
+        from . import wire
+        out = (lambda a, kind: wire.pack(a, kind)) if self.wire_format else (lambda a, kind: a)
+        inp = (lambda m, kind: wire.unpack(m, kind) if isinstance(m, (bytes, bytearray, memoryview)) else m)
+        z_enc = inp(await self.communicator.recv(self.other_party, msg_id=f"step_1_session_{session_id}"), wire.KIND_PAILLIER_CT)
         z, _beta = KeyHolder.step_2(z_enc, l, self.scheme_paillier)
         db_enc = KeyHolder.steps_4a_4b(z, l, self.scheme_dgk, self.scheme_paillier, rho=nonces.get("rho_db"), randomize=True)
-        await self.communicator.send(self.other_party, db_enc, msg_id=f"step_4b_session_{session_id}")
-        c_is_enc = await self.communicator.recv(self.other_party, msg_id=f"step_4i_session_{session_id}")
+        await self.communicator.send(self.other_party, out(db_enc, wire.KIND_DGK_VECTOR), msg_id=f"step_4b_session_{session_id}")
+        c_is_enc = inp(await self.communicator.recv(self.other_party, msg_id=f"step_4i_session_{session_id}"), wire.KIND_DGK_VECTOR)
         _delta_b, enc3 = KeyHolder.steps_4j_5(c_is_enc, z, l, self.scheme_dgk, self.scheme_paillier, rho=nonces.get("rho_enc3"), randomize=True)
-        await self.communicator.send(self.other_party, enc3, msg_id=f"step_5_session_{session_id}")
+        await self.communicator.send(self.other_party, out(enc3, wire.KIND_PAILLIER_TRIPLE), msg_id=f"step_5_session_{session_id}")
 
     async def make_and_send_encryption_schemes(self, session_id: int = 1, key_length_paillier: int = 2048, v_bits_dgk: int = 160,
                                                n_bits_dgk: int = 2048) -> None:
@@ -65,8 +69,13 @@ class KeyHolder:
             raise ValueError("Communicator not properly initialized.")
         if self._scheme_paillier is None or self._scheme_dgk is None:
             raise ValueError("No scheme has been initialized: the batched KeyHolder does not generate keys (host-side, one-off).")
-        pub = lambda s: s.public_only() if hasattr(s, "public_only") else s  # noqa: E731
-        await self.communicator.send(self.other_party, (pub(self.scheme_paillier), pub(self.scheme_dgk)), msg_id=f"schemes_session_{session_id}")
+        if self.wire_format:
+            from . import wire
+            message = wire.pack_schemes(self.scheme_paillier, self.scheme_dgk)      # public parts only, one blob
+        else:
+            pub = lambda s: s.public_only() if hasattr(s, "public_only") else s  # noqa: E731
+            message = (pub(self.scheme_paillier), pub(self.scheme_dgk))
+        await self.communicator.send(self.other_party, message, msg_id=f"schemes_session_{session_id}")
 
     # ------------------------------------------------------------------ steps
     @staticmethod
