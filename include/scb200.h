@@ -154,6 +154,30 @@ int scb_paillier_decrypt_dev(scb_ctx* ctx, const uint32_t* c, uint32_t* out, siz
 int scb_dgk_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M);
 int scb_dgk_is_zero_dev(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M);
 
+/* ---- device-side CSPRNG for the nonces ---------------------------------------------------------------------
+ * Replaces, at batch scale, secrets.randbelow / secrets.choice (initiator.py:223, 250, 420, 512) and the schemes'
+ * randomness pools (initiator.py:205-210, keyholder.py:174-179): ChaCha20 in counter mode on the device, keyed from
+ * the host, one independent keystream position per (call, element, attempt, block); uniform values below a bound by
+ * rejection sampling.  Outputs are deterministic functions of (key, nonce, call order).  The arrays feed the
+ * *_dev phases directly, so production runs need no host->device nonce traffic; injected host nonces stay
+ * available for parity testing.                                                                              */
+int scb_rng_seed(scb_ctx* ctx, const uint32_t key[8], const uint32_t nonce[2]);
+/* out[e] = uniform integer in [min_one ? 1 : 0, bound), k words each (bound: HOST array of k words; out: device) */
+int scb_rng_below_dev(scb_ctx* ctx, const uint32_t* bound, int k, int min_one, uint32_t* out, size_t B);
+/* out[e] = `bits` uniform bits in `words` words (DGK randomizer exponents rho) */
+int scb_rng_bits_dev(scb_ctx* ctx, int bits, int words, uint32_t* out, size_t B);
+/* out[e] = uniform bit (delta_A = randbelow(2)) */
+int scb_rng_coins_dev(scb_ctx* ctx, uint8_t* out, size_t B);
+/* out[e][0..n) = uniform permutation of 0..n-1 (the shuffle of step_4i: output position k takes element out[e][k]) */
+int scb_rng_permutations_dev(scb_ctx* ctx, int n, uint8_t* out, size_t B);
+/* one raw ChaCha20 block for explicit state words 12..15 (known-answer tests against RFC 8439) */
+int scb_rng_chacha_block_dev(scb_ctx* ctx, const uint32_t counter_nonce[4], uint32_t* out16);
+/* host-buffer convenience: run one of the generators above and copy the result back.
+ *   SCB_RNG_BELOW: (bound, k, arg = min_one)   SCB_RNG_BITS: (k = words, arg = bits)   SCB_RNG_COINS
+ *   SCB_RNG_PERMUTATIONS: (arg = n)            SCB_RNG_BLOCK: (bound = counter_nonce[4])                     */
+enum { SCB_RNG_BELOW = 0, SCB_RNG_BITS = 1, SCB_RNG_COINS = 2, SCB_RNG_PERMUTATIONS = 3, SCB_RNG_BLOCK = 4 };
+int scb_rng_fetch(scb_ctx* ctx, int what, const uint32_t* bound, int k, int arg, void* out_host, size_t B);
+
 /* ---- fused protocol phases (one call per party-phase of perform_secure_comparison) -------------------
  * Layouts: Paillier ciphertexts [..][2kN]; Paillier plaintexts / r / Paillier nonces rho [..][kN]; DGK
  * ciphertexts [..][kn]; per-comparison DGK vectors are [B][l+1][kn] with element 0 = [d] and elements

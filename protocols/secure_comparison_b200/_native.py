@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libscb200.so")
 OPT_PAILLIER_CRT = 1
 OPT_FIXED_BASE_WIDE = 2
 OPT_MODEXP_FP64 = 3
+RNG_BELOW, RNG_BITS, RNG_COINS, RNG_PERMUTATIONS, RNG_BLOCK = 0, 1, 2, 3, 4
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 
 MOD_PAILLIER_N2, MOD_PAILLIER_N, MOD_DGK_N, MOD_DGK_P = 0, 1, 2, 3
@@ -54,6 +55,13 @@ _SIGNATURES = {
     "scb_set_option": ([_vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_dgk_set_public": ([_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_dgk_set_private": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
+    "scb_rng_seed": ([_vp, _vp, _vp], ctypes.c_int),
+    "scb_rng_below_dev": ([_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_rng_bits_dev": ([_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_rng_coins_dev": ([_vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_rng_permutations_dev": ([_vp, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_rng_chacha_block_dev": ([_vp, _vp, _vp], ctypes.c_int),
+    "scb_rng_fetch": ([_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_paillier_encrypt": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_paillier_encrypt_dev": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_paillier_decrypt": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),

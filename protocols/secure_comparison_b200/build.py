@@ -11,12 +11,12 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "scb200.cu"), os.path.join(HERE, "csrc", "scb200_protocol.cu")]
+SRC = [os.path.join(HERE, "csrc", "scb200.cu"), os.path.join(HERE, "csrc", "scb200_protocol.cu"), os.path.join(HERE, "csrc", "scb200_rng.cu")]
 LIB = os.path.join(HERE, "libscb200.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "scb200.h")]
 
-NVCC_FLAGS = ["--threads", "2", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["--threads", "3", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 
 def needs_build() -> bool:

@@ -63,6 +63,10 @@ struct scb_ctx {
   bool profiling = false;
   std::vector<std::pair<std::string, cudaEvent_t>> prof_events;
 
+  // device CSPRNG (scb200_rng.cu): ChaCha20 key / nonce from the host, one stream per draw call
+  uint32_t rng_key[8] = {0}, rng_nonce[2] = {0, 0}, rng_call = 0;
+  bool rng_seeded = false;
+
   // ticket counters of the dynamically scheduled kernels (GroupIndex::next): a ring of device words, one zeroed per launch
   unsigned long long* queue_ring = nullptr;
   int queue_next = 0;

@@ -82,6 +82,62 @@ class Engine:
         self._check(self.lib.scb_profile_end(self.ctx, buf, len(buf)))
         return json.loads(buf.value.decode())
 
+    # ------------------------------------------------------------------ device CSPRNG (nonces)
+    def rng_seed(self, key: Optional[bytes] = None, nonce: Optional[bytes] = None) -> None:
+        """Key the device ChaCha20 generator (32-byte key, 8-byte nonce; default: fresh from ``secrets``)."""
+        import secrets
+        key = secrets.token_bytes(32) if key is None else bytes(key)
+        nonce = secrets.token_bytes(8) if nonce is None else bytes(nonce)
+        if len(key) != 32 or len(nonce) != 8:
+            raise ValueError("key must be 32 bytes and nonce 8 bytes")
+        k = np.frombuffer(key, dtype="<u4").astype(np.uint32)
+        n = np.frombuffer(nonce, dtype="<u4").astype(np.uint32)
+        self._check(self.lib.scb_rng_seed(self.ctx, nat._ptr(k), nat._ptr(n)))
+
+    def rng_below(self, bound: int, B: int, k: Optional[int] = None, min_one: bool = False, out=None) -> Optional[np.ndarray]:
+        """``[B][k]`` uniform integers in ``[min_one, bound)``.  ``out``: a device buffer (anything with ``data_ptr()``)
+        to fill in place; without it the values are copied back to a numpy array."""
+        k = k or limbs_for_bits(bound.bit_length())
+        bw = int_to_limbs(bound, k)
+        if out is not None:
+            self._check(self.lib.scb_rng_below_dev(self.ctx, nat._ptr(bw), k, int(min_one), nat._ptr(out), B))
+            return None
+        host = np.empty((B, k), dtype=np.uint32)
+        self._check(self.lib.scb_rng_fetch(self.ctx, nat.RNG_BELOW, nat._ptr(bw), k, int(min_one), nat._ptr(host), B))
+        return host
+
+    def rng_bits(self, bits: int, B: int, words: Optional[int] = None, out=None) -> Optional[np.ndarray]:
+        words = words or limbs_for_bits(bits)
+        if out is not None:
+            self._check(self.lib.scb_rng_bits_dev(self.ctx, bits, words, nat._ptr(out), B))
+            return None
+        host = np.empty((B, words), dtype=np.uint32)
+        self._check(self.lib.scb_rng_fetch(self.ctx, nat.RNG_BITS, None, words, bits, nat._ptr(host), B))
+        return host
+
+    def rng_coins(self, B: int, out=None) -> Optional[np.ndarray]:
+        if out is not None:
+            self._check(self.lib.scb_rng_coins_dev(self.ctx, nat._ptr(out), B))
+            return None
+        host = np.empty((B,), dtype=np.uint8)
+        self._check(self.lib.scb_rng_fetch(self.ctx, nat.RNG_COINS, None, 0, 0, nat._ptr(host), B))
+        return host
+
+    def rng_permutations(self, n: int, B: int, out=None) -> Optional[np.ndarray]:
+        if out is not None:
+            self._check(self.lib.scb_rng_permutations_dev(self.ctx, n, nat._ptr(out), B))
+            return None
+        host = np.empty((B, n), dtype=np.uint8)
+        self._check(self.lib.scb_rng_fetch(self.ctx, nat.RNG_PERMUTATIONS, None, 0, n, nat._ptr(host), B))
+        return host
+
+    def rng_block(self, state12_15) -> np.ndarray:
+        """One raw ChaCha20 block for explicit state words 12..15 (known-answer tests)."""
+        cn = np.asarray(state12_15, dtype=np.uint32)
+        host = np.empty((16,), dtype=np.uint32)
+        self._check(self.lib.scb_rng_fetch(self.ctx, nat.RNG_BLOCK, nat._ptr(cn), 0, 0, nat._ptr(host), 1))
+        return host
+
     # ------------------------------------------------------------------ moduli
     def load_modulus(self, slot: int, modulus: int, k32: Optional[int] = None) -> int:
         """Load an odd modulus; returns the limb count ``k32`` every operand of this slot must have."""
