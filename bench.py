@@ -47,8 +47,8 @@ MAC_PER_COMPARISON_L16 = 567e6      # reference-faithful operation list of one i
 MAC_PER_MODEXP_4096_2048 = 81.91e6  # one rho^N mod N^2 (k = 128 limbs, 2048-bit exponent)
 # fixed (x, y) pairs of the reference's tests (test_secure_comparison.py:27-37), non-negative ones
 FIXED_PAIRS = [(0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7804), (8668, 9015), (23, 42), (42, 23), (7, 7), (0, 0)]
-# ncu --set full of k_step1<18,8> at B = 32768 (profiles/r01e_ncu_k_step1.txt): dram read + write bytes per launch
-NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (4.888848e9 + 1.476549e9) / 32768
+# ncu --set full of k_modexp52<10,8> at B = 32768 (profiles/r01p_ncu_k_modexp52_10x8.txt): dram read + write bytes per launch
+NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (4.588519e9 + 1.427151e9) / 32768
 
 
 def parse_args():
@@ -273,7 +273,7 @@ def run_ours(args):
     fp64_ops = B * 2458 * (2 * 80 * 80 * 3 + 80 * 4)        # DFMA/DADD thread-instructions of one launch (2,458 products of 80 digits)
     roofline = {
         "bound": "multiplier pipes, not hbm and not tensor: " + (
-            "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; dispatch-limited: an FP64 instruction takes two issue slots)"
+            "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; throughput-limited on the DFMA + IADD3 instruction mix)"
             if fp64_engine else "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy)"),
         "kernel": k1_name if fp64_engine else "k_step1<18,8>", "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
         "kernel_ms_per_launch": round(k1_ms, 3),
@@ -283,8 +283,9 @@ def run_ours(args):
                        "pct_of_peak refers to; the IMAD microbenchmark on this pool sustains 8.6 TMAC/s, profiles/r01_imad_microbench2.jsonl)",
         "frac_of_measured_microbench_peak": round(achieved * 1e12 / INT_PEAK_MEASURED_MAC_PER_S, 4),
         "fp64_pipe_frac": round(fp64_ops / (k1_ms * 1e-3) / (148 * 64 * 1.965e9), 4) if (fp64_engine and k1_ms) else None,
-        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 55 %, "
-                          "issue slots 59 % + one extra dispatch cycle per FP64 instruction (profiles/r01m_ncu_k_modexp52.txt)",
+        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 59 %, "
+                          "ALU pipe 47 %, issue slots 57 % (profiles/r01p_ncu_k_modexp52_10x8.txt); a pure DFMA stream sustains 54.5/clk/SM, mixed 1:1 with "
+                          "integer adds 46.7 (profiles/r01_fp64_issue_microbench.jsonl)",
         "imad_engine_reference": "same launch on the IMAD engine: 833 ms at B=65536 = 6.45 TMAC/s algorithmic, fmaheavy pipe 84-87 % busy (profiles/r01e_ncu_k_step1.txt)",
         "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
         "traffic_note": "dram bytes per launch scaled from an ncu capture (window tables of the ~9,500 resident groups exceed L2): "
