@@ -55,48 +55,33 @@ def test_samplers_match_model(setup):
 
 def test_protocol_pass_with_device_nonces(setup):
     """All nonces generated on the GPU (fresh key from `secrets`), device-pointer phases end to end."""
-    import torch
+    from helpers import run_device_pass
     paillier, dgk, eng = setup
     l, B = 16, 512
-    eng.rng_seed()
     rng = np.random.default_rng(3)
     x = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
     y = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
     x[:3], y[:3] = [23, 42, 7], [42, 23, 7]
-    plain = np.zeros((2, B, eng.kN), dtype=np.uint32)
-    plain[0, :, 0], plain[1, :, 0] = x.astype(np.uint32), y.astype(np.uint32)
-    N = paillier.public_key.n
-    i32 = dict(dtype=torch.int32, device="cuda")
-    dev = lambda *shape: torch.empty(shape, **i32)  # noqa: E731
-    d_rho_in, d_r, d_rho_z, d_rho3 = dev(2 * B, eng.kN), dev(B, eng.kN), dev(B, eng.kN), dev(3 * B, eng.kN)
-    d_rblind, d_rho_c, d_rho_db = dev(B * (l + 1), eng.rb_words), dev(B * (l + 1), eng.rand_words), dev(B * (l + 1), eng.rand_words)
-    d_da = torch.empty((B,), dtype=torch.uint8, device="cuda")
-    d_perm = torch.empty((B, l + 1), dtype=torch.uint8, device="cuda")
-    eng.rng_below(N, 2 * B, eng.kN, True, out=d_rho_in)
-    eng.rng_below(N, B, eng.kN, False, out=d_r)                                   # r = randbelow(N)
-    eng.rng_below(N, B, eng.kN, True, out=d_rho_z)
-    eng.rng_below(N, 3 * B, eng.kN, True, out=d_rho3)
-    eng.rng_below(dgk.public_key.u, B * (l + 1), eng.rb_words, True, out=d_rblind)  # r_i in [1, u-1]
-    eng.rng_bits(dgk.randomness_bits, B * (l + 1), eng.rand_words, out=d_rho_c)
-    eng.rng_bits(dgk.randomness_bits, B * (l + 1), eng.rand_words, out=d_rho_db)
-    eng.rng_coins(B, out=d_da)
-    eng.rng_permutations(l + 1, B, out=d_perm)
-    d_plain = torch.from_numpy(plain.reshape(2 * B, eng.kN).view(np.int32)).cuda()
-    d_in, d_z_enc, d_z = dev(2 * B, eng.kc), dev(B, eng.kc), dev(B, eng.kN)
-    d_db, d_c, d_enc3, d_res, d_bit = dev(B, l + 1, eng.kn), dev(B, l + 1, eng.kn), dev(B, 3, eng.kc), dev(B, eng.kc), dev(B, eng.kN)
-    d_delta_b = torch.empty((B,), dtype=torch.uint8, device="cuda")
-    lib, ctx, p = eng.lib, eng.ctx, nat._ptr
-    torch.cuda.synchronize()
-    eng._check(lib.scb_paillier_encrypt_dev(ctx, p(d_plain), p(d_rho_in), p(d_in), 2 * B))
-    eng._check(lib.scb_initiator_step1_dev(ctx, p(d_in[:B]), p(d_in[B:]), p(d_r), p(d_rho_z), l, p(d_z_enc), B))
-    eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_z_enc), p(d_z), B))
-    eng._check(lib.scb_keyholder_step4ab_dev(ctx, p(d_z), l, p(d_rho_db), eng.rand_words, p(d_db), B))
-    eng._check(lib.scb_initiator_step4_dev(ctx, p(d_db), p(d_r), p(d_da), p(d_rblind), eng.rb_words, p(d_perm), p(d_rho_c), eng.rand_words, l, p(d_c), B))
-    eng._check(lib.scb_keyholder_step4j_5_dev(ctx, p(d_c), p(d_z), p(d_rho3), l, p(d_delta_b), p(d_enc3), B))
-    eng._check(lib.scb_initiator_step6_7_dev(ctx, p(d_enc3), p(d_r), p(d_da), l, p(d_res), B))
-    eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_res), p(d_bit), B))
-    eng.sync()
-    bits = d_bit.cpu().numpy().view(np.uint32)
+    bits, r_vals = run_device_pass(eng, paillier, dgk, l, x, y)
     assert np.array_equal(bits[:, 0].astype(np.uint8), (x <= y).astype(np.uint8)) and not bits[:, 1:].any()
-    r_vals = limbs_to_ints(d_r.cpu().numpy().view(np.uint32))
-    assert len(set(r_vals)) == B and all(v < N for v in r_vals)
+    assert len(set(r_vals)) == B and all(v < paillier.public_key.n for v in r_vals)
+
+
+@pytest.mark.parametrize("pbits,dbits,vbits,l,B", [(2048, 2048, 160, 16, 8192), (2048, 2048, 160, 32, 4096), (4096, 3072, 160, 64, 1024)])
+def test_larger_batches_decrypt_to_the_truth(pbits, dbits, vbits, l, B):
+    """Property check at sizes the oracle cannot follow (BASELINE configs[1..3] key sizes and bit lengths): every decrypted
+    comparison bit equals the plaintext truth, with equal pairs, extremes and adjacent values forced in."""
+    from helpers import run_device_pass
+    paillier, dgk = make_schemes(pbits, dbits, vbits, l)
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    rng = np.random.default_rng(l)
+    hi = (1 << l) - 1
+    x = rng.integers(0, hi, size=B, dtype=np.uint64, endpoint=True)
+    y = rng.integers(0, hi, size=B, dtype=np.uint64, endpoint=True)
+    y[: B // 8] = x[: B // 8]                                        # equal pairs
+    y[B // 8: B // 4] = np.minimum(x[B // 8: B // 4], np.uint64(hi - 1)) + np.uint64(1)     # y = x + 1
+    x[-4:], y[-4:] = [0, hi, 0, hi], [0, hi, hi, 0]
+    bits, _ = run_device_pass(eng, paillier, dgk, l, x, y)
+    assert not bits[:, 1:].any()
+    assert np.array_equal(bits[:, 0].astype(np.uint8), (x <= y).astype(np.uint8))
