@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -324,7 +325,13 @@ int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, 
                     const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   using G = Geo52<L, TPI>;
   const int wbits = window_bits_for(ebits);
-  const size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  // tuning aid: SCB_F64_EXTRA_SMEM=<bytes> pads the dynamic shared memory to lower the number of resident blocks
+  static const size_t extra_smem = getenv("SCB_F64_EXTRA_SMEM") ? static_cast<size_t>(atol(getenv("SCB_F64_EXTRA_SMEM"))) : 0;
+  if (extra_smem) {
+    smem += extra_smem;
+    cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_modexp52<L, TPI>), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
   const int gpb = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
   int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_modexp52<L, TPI>), smem, B, gpb);
   void* scratch = nullptr;
