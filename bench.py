@@ -34,9 +34,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "secure comparisons/sec (Paillier-2048/DGK-2048, l=16)"
+METRIC = "secure comparisons/sec (Paillier-2048/DGK-2048, l=16)"   # the headline configuration; other --l / key sizes are labelled in `config`
 UNIT = "comparisons/s"
 KEY_FILE = os.path.join(ROOT, "tests", "golden", "keys_p2048_d2048_v160_l16.json")   # seeded synthetic key pair (data)
+
+
+def key_file(paillier_bits: int, dgk_bits: int, l: int) -> str:
+    """Seeded synthetic key pairs (data, committed under tests/golden): the headline configuration and the key sizes /
+    bit lengths of BASELINE configs[2] (l = 32) and configs[3] (Paillier-4096 / DGK-3072, l = 64)."""
+    return os.path.join(ROOT, "tests", "golden", f"keys_p{paillier_bits}_d{dgk_bits}_v160_l{l}.json")
 # Integer-multiply peak: IMAD.WIDE.U32 (32x32+64 -> 64) issues on the fmaheavy pipe only, 8 lanes/clk/SMSP =
 # 32 MAC/clk/SM (ncu: sm__pipe_fmaheavy_cycles_active; microbenchmark profiles/r01_imad_microbench2.jsonl measured
 # 8.6 TMAC/s sustained = 29.6/clk/SM at the nominal clock).  Peak used for `frac` = 148 SMs x 32 x 1.965 GHz.
@@ -59,6 +65,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="comparisons per GPU per step")
     ap.add_argument("--l", type=int, default=16)
+    ap.add_argument("--paillier-bits", type=int, default=2048)
+    ap.add_argument("--dgk-bits", type=int, default=2048)
     ap.add_argument("--cpu-per-core", type=int, default=40, help="comparisons per host core in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -138,8 +146,9 @@ def make_workload(B: int, l: int, seed: int, eng):
 
     rand_bits_n = eng._fixed_base[0][1]
     u = eng.u
-    r_blind = np.zeros((B, l + 1, eng.rb_words), dtype=np.uint32)
-    r_blind[..., 0] = rng.integers(1, min(u, 1 << 32), size=(B, l + 1), dtype=np.uint64).astype(np.uint32)   # in [1, u-1] (u < 2^32 for l <= 29)
+    # blinding exponents in [1, u-1]: odd values below 2^(bitlen(u)-1) (a subset of the range; the arithmetic is the same)
+    r_blind = rand_bits((B, l + 1, eng.rb_words), u.bit_length() - 1)
+    r_blind[..., 0] |= 1
     perm = np.argsort(rng.random((B, l + 1)), axis=1).astype(np.uint8)
     plain = np.zeros((2, B, kN), dtype=np.uint32)
     plain[0, :, 0] = (x & 0xFFFFFFFF).astype(np.uint32)
@@ -182,7 +191,7 @@ def run_ours(args):
     # weak scaling: the global batch is world * B comparisons; this rank owns the contiguous block [lo, hi)
     lo, hi = shard_range(world * B, rank, world)
     assert hi - lo == B
-    paillier, dgk = schemes_from_json(KEY_FILE)
+    paillier, dgk = schemes_from_json(key_file(args.paillier_bits, args.dgk_bits, l))
     eng = SchemeEngine(local)
     eng.load_paillier(paillier)
     eng.load_dgk(dgk, l)
@@ -263,19 +272,24 @@ def run_ours(args):
     top_name = max(kernels, key=lambda k: kernels[k]["ms"])
     # the B modexps rho^N mod N^2 of Initiator.step_1 + randomize: one launch of k_modexp52<10,8> (FP64 engine, default) or,
     # with the IMAD engine, the modexp fused inside k_step1<18,8>
-    fp64_engine = "k_modexp52<10,8>[e=2048]" in kernels
-    k1_name = "k_modexp52<10,8>[e=2048]" if fp64_engine else "k_step1"
+    ebits_N = eng.paillier_n.bit_length()
+    f64_names = [k for k in kernels if k.startswith("k_modexp52") and k.endswith(f"[e={ebits_N}]")]
+    fp64_engine = bool(f64_names)
+    k1_name = f64_names[0] if fp64_engine else "k_step1"
     k1 = kernels.get(k1_name, {"ms": 0.0, "launches": 1})
     k1_ms = k1["ms"] / max(k1["launches"], 1)
-    k1_mac = B * MAC_PER_MODEXP_4096_2048                 # algorithmic: B randomizers rho^N mod N^2
+    # algorithmic MACs of B randomizers rho^N mod N^2 (SURVEY 8d formula; 81.91 M each at Paillier-2048)
+    k1_mac = B * (ebits_N + -(-ebits_N // 5) + 32) * (2 * kc * kc + kc)
     achieved = k1_mac / (k1_ms * 1e-3) / 1e12 if k1_ms else 0.0
     bytes_per_launch = B * (kN * 4 + kc * 4) if fp64_engine else B * (2 * kc * 4 + 2 * kN * 4 + kc * 4)
-    fp64_ops = B * 2458 * (2 * 80 * 80 * 3 + 80 * 4)        # DFMA/DADD thread-instructions of one launch (2,458 products of 80 digits)
+    K52 = {4096: 80, 8192: 160}.get(64 * kN, (64 * kN + 4 + 51) // 52)
+    nprod = ebits_N + -(-ebits_N // 6) + 64                 # squarings + 6-bit-window products + table (2,455 at 2048 bits)
+    fp64_ops = B * nprod * (2 * K52 * K52 * 3 + K52 * 4)    # DFMA/DADD thread-instructions of one launch
     roofline = {
         "bound": "multiplier pipes, not hbm and not tensor: " + (
             "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; throughput-limited on the DFMA + IADD3 instruction mix)"
             if fp64_engine else "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy)"),
-        "kernel": k1_name if fp64_engine else "k_step1<18,8>", "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
+        "kernel": k1_name, "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
         "kernel_ms_per_launch": round(k1_ms, 3),
         "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic)",
         "frac": round(achieved * 1e12 / INT_PEAK_MAC_PER_S, 4),
@@ -374,7 +388,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: 52-bit digits in f64 (exponentiations) + 29-bit digits in u32/u64 (everything else)",
             "data": "synthetic (seeded keys, inputs and host-supplied nonces)",
-            "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-2048/DGK-2048 (v=160), interactive flow (all randomize() calls)",
+            "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-{args.paillier_bits}/DGK-{args.dgk_bits} (v=160), interactive flow (all randomize() calls)",
                        "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l,
                        "sharding": "contiguous block of the global batch per rank, no data-path collective"},
             "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},

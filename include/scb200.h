@@ -109,6 +109,11 @@ int scb_fixed_base_exp(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_wor
 int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp_words, const uint32_t* mul_in,
                            uint32_t* out, size_t B);
 
+/* Test hook (not part of the product surface): the exact carry resolution that ends every product of the FP64 engine,
+ * on crafted column values.  cols: [G][40] column sums (< 2^63), hi: [G][4] extra high accumulator per lane, out: [G][40]
+ * normalised 52-bit digits.  Its second-order ripple path is unreachable with random operands, so tests drive it here. */
+int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G);
+
 /* ---- scheme keys ------------------------------------------------------------------------------------
  * Replace the scheme objects the reference threads through every step (tno.mpc.encryption_schemes
  * Paillier / DGK: public_key.{n, n_squared, g} / secret_key.{lambda_, mu}; public_key.{n, g, h, u, t} /

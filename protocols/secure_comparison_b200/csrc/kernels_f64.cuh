@@ -155,6 +155,31 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
   for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
 }
 
+// Test hook for the carry resolution of the FP64 engine (its second-order ripple loop has probability ~2^-52 per
+// product on random data, so the parity tests never reach it): cols [G][K] column values, hi [G][TPI] the extra
+// high accumulator of each lane, out [G][K] the normalised 52-bit digits.  One warp per GPW numbers.
+template <int L, int TPI>
+__global__ void k_debug_resolve52(const uint64_t* __restrict__ cols, const uint64_t* __restrict__ hi, uint64_t* __restrict__ out, size_t G) {
+  constexpr int K = Geo52<L, TPI>::K;
+  constexpr int GPW = Geo52<L, TPI>::GPW;
+  const int lane = threadIdx.x & 31, t = lane % TPI;
+  const size_t rounds = (G + GPW - 1) / GPW;
+  for (size_t rd = 0; rd < rounds; rd++) {
+    size_t g = rd * GPW + lane / TPI;
+    const bool active = g < G;
+    if (!active) g = G - 1;
+    uint64_t col[L];
+    double r[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) col[i] = cols[g * K + t * L + i];
+    resolve_carries<L, TPI>(col, hi[g * TPI + t], r);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < L; i++) out[g * K + t * L + i] = double_to_u52(r[i]);
+    }
+  }
+}
+
 // out[i] = (mul_in[i] *) base[i]^exp[i] mod n
 // registers: L = 10 needs ~150 (3 blocks of 128 threads per SM: measured 3 % faster than 4 blocks with a few spills),
 // L = 15 needs ~230 (2 blocks per SM)

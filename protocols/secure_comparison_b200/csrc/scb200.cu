@@ -574,6 +574,29 @@ extern "C" int scb_modinv_dev(scb_ctx* ctx, int slot, const uint32_t* a, uint32_
   return modinv_dev_raw(ctx, slot, a, out, ok, B);
 }
 
+// test hook: carry resolution of the FP64 engine on crafted column values (K = 40: 10 digits x 4 lanes)
+extern "C" int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G) {
+  if (!ctx || !cols || !hi || !out) return SCB_EINVAL;
+  if (G == 0) return SCB_OK;
+  cudaSetDevice(ctx->device);
+  constexpr int K = 40, TPI = 4;
+  void* dev = nullptr;
+  const size_t nb_cols = sizeof(uint64_t) * G * K, nb_hi = sizeof(uint64_t) * G * TPI;
+  int rc = ctx->scratch(2, 2 * nb_cols + nb_hi + 1024, &dev);
+  if (rc) return rc;
+  uint64_t* dcols = static_cast<uint64_t*>(dev);
+  uint64_t* dout = dcols + G * K;
+  uint64_t* dhi = dout + G * K;
+  cudaError_t e = cudaMemcpyAsync(dcols, cols, nb_cols, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dhi, hi, nb_hi, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D copy");
+  k_debug_resolve52<10, 4><<<1, 32, 0, ctx->stream>>>(dcols, dhi, dout, G);
+  if ((rc = ctx->launched("k_debug_resolve52"))) return rc;
+  e = cudaMemcpyAsync(out, dout, nb_cols, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H copy");
+  return scb_sync(ctx);
+}
+
 extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint32_t* base, int exp_bits) {
   int rc = check_mod(ctx, slot, "scb_fixed_base_load");
   if (rc) return rc;

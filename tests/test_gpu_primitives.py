@@ -127,3 +127,35 @@ def test_argument_errors(eng):
     with pytest.raises(ValueError):
         eng.modmul(SLOT, np.zeros((3, k + 1), np.uint32), np.zeros((3, k + 1), np.uint32))
     assert eng.modmul(SLOT, np.zeros((0, k), np.uint32), np.zeros((0, k), np.uint32)).shape == (0, k)
+
+
+def test_fp64_engine_carry_resolution_rare_paths(eng):
+    """resolve_carries of the FP64 engine on crafted columns: all-ones digits with a carry arriving from below (the
+    second-order ripple loop, probability ~2^-52 per product on random data), big lane carries, mixed cases."""
+    K, TPI, L = 40, 4, 10
+    M52 = (1 << 52) - 1
+    rng = random.Random(52)
+    cases = []
+    ones = [M52] * K
+    cases.append(([1] + [0] * (K - 1), [0] * TPI))                                   # trivial
+    cases.append(([M52 + 1] + ones[1:K - 1] + [0], [0] * TPI))                        # +1 ripples through every lane to the top digit
+    cases.append(([M52 + 5] + ones[1:L] + ones[L:2 * L] + [7] + [0] * (K - 2 * L - 1), [0] * TPI))   # ripple across two lane boundaries
+    cases.append(([(1 << 58) + 3] * (K - 2) + [0, 0], [0] * TPI))                     # large column values everywhere
+    c = list(ones); c[L - 1] = M52; c[0] = M52 + 1; c[K - 1] = 0
+    cases.append((c, [0] * TPI))
+    cases.append(([M52] * (K - 1) + [0], [1, 0, 0, 0]))                                # carry enters through the lane's high accumulator
+    cases.append(([M52] * (K - 1) + [0], [(1 << 57) + 1, 1, 1, 0]))
+    for _ in range(40):
+        cols = [rng.choice([M52, M52, M52 + 1, rng.getrandbits(60), 0, 1]) for _ in range(K - 1)] + [0]
+        hi = [rng.choice([0, 1, rng.getrandbits(56)]) for _ in range(TPI - 1)] + [0]
+        cases.append((cols, hi))
+    G = len(cases)
+    cols = np.array([c for c, _ in cases], dtype=np.uint64)
+    hi = np.array([h for _, h in cases], dtype=np.uint64)
+    out = np.zeros((G, K), dtype=np.uint64)
+    eng._check(eng.lib.scb_debug_resolve52(eng.ctx, nat._ptr(cols), nat._ptr(hi), nat._ptr(out), G))
+    for (c, h), digits in zip(cases, out.tolist()):
+        value = sum(int(v) << (52 * i) for i, v in enumerate(c)) + sum(int(v) << (52 * L * (t + 1)) for t, v in enumerate(h))
+        assert value < 1 << (52 * K), "test case overflows the representation"
+        assert all(d <= M52 for d in digits)
+        assert sum(d << (52 * i) for i, d in enumerate(digits)) == value
