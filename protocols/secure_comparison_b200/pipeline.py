@@ -46,16 +46,21 @@ class PinnedArena:
 
 
 class LocalPipeline:
-    def __init__(self, scheme_paillier, scheme_dgk, l: int, device: int = 0, n_contexts: int = 2, chunks: Optional[int] = None):
+    def __init__(self, scheme_paillier, scheme_dgk, l: int, device: int = 0, n_contexts: int = 2, chunks: Optional[int] = None,
+                 devices: Optional[List[int]] = None):
+        """``devices``: run on several GPUs of the box from ONE process -- ``n_contexts`` contexts per device, one worker
+        thread per context, the batch sharded by comparison index with no device-to-device traffic.
+        Default: the single GPU ``device``."""
         self.l = l
         self.engines = []
-        for _ in range(n_contexts):
-            eng = SchemeEngine(device)
-            eng.load_paillier(scheme_paillier)
-            eng.load_dgk(scheme_dgk, l)
-            self.engines.append(eng)
-        self.chunks = chunks if chunks is not None else n_contexts
-        self.pool = ThreadPoolExecutor(max_workers=n_contexts)
+        for dev in (devices if devices is not None else [device]):
+            for _ in range(n_contexts):
+                eng = SchemeEngine(dev)
+                eng.load_paillier(scheme_paillier)
+                eng.load_dgk(scheme_dgk, l)
+                self.engines.append(eng)
+        self.chunks = chunks if chunks is not None else 2 * len(self.engines)
+        self.pool = ThreadPoolExecutor(max_workers=len(self.engines))
         self.arena = PinnedArena()
         self._bufs: Dict[tuple, dict] = {}
 

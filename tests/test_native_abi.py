@@ -40,3 +40,30 @@ def test_limb_round_trip():
     assert arr[2].tolist() == [0xFFFFFFFF] * 64
     with pytest.raises(OverflowError):
         ints_to_limbs([1 << 64], 2)
+
+
+def _compile_c_smoke(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(nat.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_smoke.c"),
+           "-L", libdir, "-lscb200", f"-Wl,-rpath,{libdir}", "-o", exe]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return exe
+
+
+def test_header_compiles_as_c99_and_links(tmp_path):
+    """include/scb200.h is plain C (no C++-isms) and a C program links against the shared library."""
+    from protocols.secure_comparison_b200.build import build
+    build()
+    _compile_c_smoke(tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_program_runs_the_abi(tmp_path):
+    import subprocess
+    exe = _compile_c_smoke(tmp_path)
+    proc = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "c_abi_smoke ok" in proc.stdout
