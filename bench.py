@@ -57,6 +57,15 @@ FIXED_PAIRS = [(0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7
 NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (4.588519e9 + 1.427151e9) / 32768
 
 
+def _measured_hbm_gbs() -> float:
+    """HBM copy bandwidth measured by the driver on this pool (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,6 +313,8 @@ def run_ours(args):
         "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
         "traffic_note": "dram bytes per launch scaled from an ncu capture (window tables of the ~9,500 resident groups exceed L2): "
                         "tens of GB/s, non-binding next to hbm_gbs = 6,550",
+        "hbm_peak_gbs_measured": _measured_hbm_gbs(),
+        "hbm_frac_of_measured": round(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B / (k1_ms * 1e-3) / 1e9 / _measured_hbm_gbs(), 5) if k1_ms else None,
         "algorithmic_bytes": int(bytes_per_launch),
         "hbm_gbs_algorithmic": round(bytes_per_launch / (k1_ms * 1e-3) / 1e9, 2) if k1_ms else None,
         "whole_step_frac": round(value / world * MAC_PER_COMPARISON_L16 / INT_PEAK_MAC_PER_S, 4),

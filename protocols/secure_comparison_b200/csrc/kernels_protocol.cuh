@@ -379,7 +379,7 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   const int kN = keys->kN;
   uint32_t* X = scratch + slot * modexp_scratch_words<L, TPI>(wbits);
   uint32_t* ACC = X + K;
@@ -438,7 +438,7 @@ k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, cons
     mm<L, TPI>(m, g.sm, X, X, xinv + i * K);
     mm<L, TPI>(m, g.sm, TMP, X, TMP);
     if (rho != nullptr) {
-      // keep Z in the output buffer's slot? no: park it in table[0..K) is unsafe (table is rebuilt) -> use ACC after the modexp
+      // park Z in the extra slot behind the window tables: X, ACC, TMP and the table are all rewritten by the exponentiation
       uint32_t* Z = scratch + (total * modexp_scratch_words<L, TPI>(wbits)) + slot * K;   // one extra slot per group behind the tables
       copy_digits(g, Z, TMP);
       words_to_digits(g, TMP, rho + i * kN, kN);
@@ -588,7 +588,7 @@ k_step4_main(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys,
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(m, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   const int kn = keys->kn;
   const size_t stride = step4_scratch_words<L, TPI>(l, wbits);
   size_t i;
@@ -783,7 +783,7 @@ k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ key
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
   const Grp<L, TPI> g = grp_init<L, TPI>(mp, GI::warp_smem(smem));
-  const size_t slot = GI::slot(), total = GI::total();
+  const size_t slot = GI::slot();
   const int kn = keys->kn;
   uint32_t* X = scratch + slot * modexp_scratch_words<L, TPI>(wbits);
   uint32_t* ACC = X + K;
