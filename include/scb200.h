@@ -132,6 +132,8 @@ int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, const uint32_t
 enum {
   SCB_OPT_PAILLIER_CRT = 1,     /* KeyHolder Paillier work over p, p^2, q, q^2 (default 1 when the primes are loaded) */
   SCB_OPT_FIXED_BASE_WIDE = 2,  /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
+  SCB_OPT_SLIDING_WINDOWS = 4,  /* sliding-window programs for the shared exponents the library owns (N, CRT exponents, v_p, lambda) on the
+                                   FP64 engine (default 1; 0 = fixed windows everywhere) */
   SCB_OPT_MODEXP_FP64 = 3       /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
                                    the IMAD one (default 1; results are bit-identical either way) */
 };

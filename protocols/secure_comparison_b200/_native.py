@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libscb200.so")
 OPT_PAILLIER_CRT = 1
 OPT_FIXED_BASE_WIDE = 2
 OPT_MODEXP_FP64 = 3
+OPT_SLIDING_WINDOWS = 4
 RNG_BELOW, RNG_BITS, RNG_COINS, RNG_PERMUTATIONS, RNG_BLOCK = 0, 1, 2, 3, 4
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 

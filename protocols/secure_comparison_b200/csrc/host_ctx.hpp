@@ -67,6 +67,18 @@ struct scb_ctx {
   uint32_t rng_key[8] = {0}, rng_nonce[2] = {0, 0}, rng_call = 0;
   bool rng_seeded = false;
 
+  // sliding-window programs of the SHARED exponents the library itself owns (N, the CRT exponents, v_p, lambda), keyed by
+  // the device address of the exponent words; consulted by modexp_any for shared-exponent launches on the FP64 engine
+  struct ExpProgram {
+    uint16_t* dev = nullptr;
+    int n = 0, w = 0;
+  };
+  std::map<const uint32_t*, ExpProgram> exp_programs;
+  bool use_sliding = true;
+  int register_exponent(const uint32_t* dev_words, const uint32_t* host_words, int nwords);
+  void clear_exponent_programs();
+  std::vector<uint32_t> crt_exp_host;
+
   // ticket counters of the dynamically scheduled kernels (GroupIndex::next): a ring of device words, one zeroed per launch
   unsigned long long* queue_ring = nullptr;
   int queue_next = 0;

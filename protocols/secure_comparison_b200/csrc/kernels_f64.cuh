@@ -155,6 +155,76 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
   for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
 }
 
+// acc = x~^e for a SHARED exponent compiled on the host into a sliding-window program (scb_ctx::register_exponent):
+//   prog[0]            = table index of the leading window
+//   prog[i], i >= 1    = (number of squarings << 8) | table index of the odd window value to multiply by (0xFF = none)
+// table[i] = x~^(2i+1), i < 2^(pw-1): one squaring (x~^2, staged once) and 2^(pw-1) - 1 products.  About 4 % fewer
+// products than the fixed-window loop for 1024..2048-bit exponents (GMP's mpz_powm, which the reference reaches through
+// gmpy2.powmod, is a sliding-window method as well).  The program is the same for the whole launch, so every branch here
+// is launch-uniform; one inlined copy of the row loop serves the three phases.
+template <int L, int TPI>
+__device__ __forceinline__ void group_modexp52_prog(const Modulus52Dev* __restrict__ m, double* sm_group, double* acc, const double* xm,
+                                                    const uint16_t* __restrict__ prog, int nprog, int pw, double* table) {
+  constexpr int K = Geo52<L, TPI>::K;
+  const int t = (threadIdx.x & 31) % TPI;
+  const int T = 1 << (pw - 1);
+  double r[L], nv[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) nv[i] = m->n[t * L + i];
+  const double np = m->np;
+#pragma unroll
+  for (int i = 0; i < L; i++) r[i] = xm[t * L + i];
+#pragma unroll
+  for (int i = 0; i < L; i++) table[t * L + i] = r[i];
+  const uint32_t idx0 = __ldg(prog);
+  int phase = 0, ti = 1, pe = 1, sq_left = 0;
+  uint32_t cur_idx = 0xFF;
+  bool need_mul = false;
+#pragma unroll 1
+  for (;;) {
+    if (phase == 0) {
+      stage_digits52<L, TPI>(sm_group, r);                       // x~ * x~
+    } else if (phase == 2) {
+      if (sq_left == 0 && !need_mul) {
+        if (pe >= nprog) break;
+        const uint32_t e = __ldg(prog + pe++);
+        sq_left = static_cast<int>(e >> 8);
+        cur_idx = e & 0xFFu;
+        need_mul = cur_idx != 0xFFu;
+        if (sq_left == 0 && !need_mul) continue;
+      }
+      if (sq_left > 0) {
+        stage_digits52<L, TPI>(sm_group, r);                     // squaring
+        sq_left--;
+      } else {
+        double bv[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) bv[i] = table[static_cast<size_t>(cur_idx) * K + t * L + i];
+        stage_digits52<L, TPI>(sm_group, bv);                    // window product
+        need_mul = false;
+      }
+    }                                                            // phase 1: x~^2 is still staged
+    mmd_rows<L, TPI>(r, nv, np, sm_group, r);
+    if (phase == 0) {
+      stage_digits52<L, TPI>(sm_group, r);                       // x~^2 stays staged for the whole table build
+#pragma unroll
+      for (int i = 0; i < L; i++) r[i] = table[t * L + i];       // back to x~
+      phase = 1;
+    } else if (phase == 1) {
+#pragma unroll
+      for (int i = 0; i < L; i++) table[static_cast<size_t>(ti) * K + t * L + i] = r[i];
+      ti++;
+    }
+    if (phase == 1 && ti == T) {
+#pragma unroll
+      for (int i = 0; i < L; i++) r[i] = table[static_cast<size_t>(idx0) * K + t * L + i];
+      phase = 2;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
+}
+
 // Test hook for the carry resolution of the FP64 engine (its second-order ripple loop has probability ~2^-52 per
 // product on random data, so the parity tests never reach it): cols [G][K] column values, hi [G][TPI] the extra
 // high accumulator of each lane, out [G][K] the normalised 52-bit digits.  One warp per GPW numbers.
@@ -187,7 +257,7 @@ template <int L, int TPI>
 __global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 3 : 2))
 k_modexp52(const Modulus52Dev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp, int ewords,
            size_t exp_stride, int ebits, int wbits, double* scratch, const uint32_t* __restrict__ mul_in, uint32_t* __restrict__ out, int kout,
-           size_t B, unsigned long long* queue) {
+           size_t B, unsigned long long* queue, const uint16_t* __restrict__ prog, int nprog, int pw) {
   extern __shared__ double smem52[];
   using GI = GroupIndex52<L, TPI>;
   constexpr int K = Geo52<L, TPI>::K;
@@ -201,7 +271,10 @@ k_modexp52(const Modulus52Dev* __restrict__ m, const uint32_t* __restrict__ base
   bool active;
   while (GI::next(queue, B, inst, active)) {
     load_mont52<L, TPI>(m, sm_group, X, TMP, base + inst * kbase, kbase);
-    group_modexp52<L, TPI>(m, sm_group, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
+    if (prog != nullptr)
+      group_modexp52_prog<L, TPI>(m, sm_group, ACC, X, prog, nprog, pw, table);
+    else
+      group_modexp52<L, TPI>(m, sm_group, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
     if (mul_in != nullptr) {
       load_mont52<L, TPI>(m, sm_group, TMP, X, mul_in + inst * kout, kout);
       mmd<L, TPI>(m, sm_group, ACC, ACC, TMP);

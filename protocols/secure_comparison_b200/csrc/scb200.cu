@@ -113,6 +113,77 @@ int scb_ctx::scratch(int which, size_t bytes, void** out) {
   return SCB_OK;
 }
 
+// Compile a shared exponent into a left-to-right sliding-window program (format: kernels_f64.cuh, group_modexp52_prog)
+// and keep it on the device, keyed by the device address of the exponent words.
+int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_words, int nwords) {
+  int top = -1;
+  for (int i = nwords - 1; i >= 0 && top < 0; i--)
+    if (host_words[i]) top = i * 32 + 31 - __builtin_clz(host_words[i]);
+  auto it = exp_programs.find(dev_words);
+  if (it != exp_programs.end()) {
+    cudaFree(it->second.dev);
+    exp_programs.erase(it);
+  }
+  if (top < 63) return SCB_OK;                     // short (or zero) exponents stay on the fixed-window loop
+  const int bits = top + 1;
+  int w = 2;
+  double best = 1e30;
+  for (int cand = 2; cand <= 7; cand++) {
+    const double cost = (1 << (cand - 1)) + static_cast<double>(bits) / (cand + 1);
+    if (cost < best) { best = cost; w = cand; }
+  }
+  auto bit = [&](int i) -> int { return (host_words[i >> 5] >> (i & 31)) & 1u; };
+  std::vector<uint16_t> prog;
+  int i = top, pending = 0;
+  bool first = true;
+  auto emit = [&](int nsq, int idx) {
+    while (nsq > 255) {
+      prog.push_back(static_cast<uint16_t>((255 << 8) | 0xFF));
+      nsq -= 255;
+    }
+    prog.push_back(static_cast<uint16_t>((nsq << 8) | idx));
+  };
+  while (i >= 0) {
+    if (!bit(i)) {
+      pending++;
+      i--;
+      continue;
+    }
+    int s = i - w + 1 < 0 ? 0 : i - w + 1;
+    while (!bit(s)) s++;
+    int val = 0;
+    for (int j = i; j >= s; j--) val = (val << 1) | bit(j);
+    const int idx = (val - 1) / 2;
+    if (first) {
+      prog.push_back(static_cast<uint16_t>(idx));
+      first = false;
+    } else {
+      emit(pending + (i - s + 1), idx);
+    }
+    pending = 0;
+    i = s - 1;
+  }
+  if (pending > 0) emit(pending, 0xFF);
+  ExpProgram ep;
+  ep.n = static_cast<int>(prog.size());
+  ep.w = w;
+  cudaError_t e = cudaMalloc(&ep.dev, sizeof(uint16_t) * prog.size());
+  if (e != cudaSuccess) return cuda_fail(this, e, "cudaMalloc(exponent program)");
+  e = cudaMemcpyAsync(ep.dev, prog.data(), sizeof(uint16_t) * prog.size(), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) {
+    cudaFree(ep.dev);
+    return cuda_fail(this, e, "upload exponent program");
+  }
+  exp_programs[dev_words] = ep;
+  return SCB_OK;
+}
+
+void scb_ctx::clear_exponent_programs() {
+  for (auto& kv : exp_programs) cudaFree(kv.second.dev);
+  exp_programs.clear();
+}
+
 unsigned long long* scb_ctx::fresh_queue() {
   constexpr int RING = 64;
   if (!queue_ring && cudaMalloc(&queue_ring, sizeof(unsigned long long) * RING) != cudaSuccess) return nullptr;
@@ -163,6 +234,7 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   if (ctx->vp_dev) cudaFree(ctx->vp_dev);
   if (ctx->crt_exp_dev) cudaFree(ctx->crt_exp_dev);
   if (ctx->queue_ring) cudaFree(ctx->queue_ring);
+  ctx->clear_exponent_programs();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -324,7 +396,19 @@ template <int L, int TPI>
 int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, int kbase, const uint32_t* exp, int ewords, size_t estride, int ebits,
                     const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   using G = Geo52<L, TPI>;
-  const int wbits = window_bits_for(ebits);
+  int wbits = window_bits_for(ebits);
+  // shared exponent with a registered sliding-window program?
+  const uint16_t* prog = nullptr;
+  int nprog = 0, pw = 0;
+  if (estride == 0 && ctx->use_sliding) {
+    auto it = ctx->exp_programs.find(exp);
+    if (it != ctx->exp_programs.end()) {
+      prog = it->second.dev;
+      nprog = it->second.n;
+      pw = it->second.w;
+      if (pw - 1 > wbits) wbits = pw - 1;          // scratch: the program's table has 2^(pw-1) entries
+    }
+  }
   size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
   // tuning aid: SCB_F64_EXTRA_SMEM=<bytes> pads the dynamic shared memory to lower the number of resident blocks
   static const size_t extra_smem = getenv("SCB_F64_EXTRA_SMEM") ? static_cast<size_t>(atol(getenv("SCB_F64_EXTRA_SMEM"))) : 0;
@@ -340,7 +424,7 @@ int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, 
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_modexp52<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev52, base, kbase, exp, ewords, estride, ebits, wbits,
-                                                                 static_cast<double*>(scratch), mul_in, out, kout, B, queue);
+                                                                 static_cast<double*>(scratch), mul_in, out, kout, B, queue, prog, nprog, pw);
   char label[64];
   snprintf(label, sizeof(label), "k_modexp52<%d,%d>[e=%d]", L, TPI, ebits);
   return ctx->launched(label);

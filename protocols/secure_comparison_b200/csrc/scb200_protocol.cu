@@ -95,6 +95,29 @@ const uint32_t* keys_N_words(scb_ctx* ctx) {
   return reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ctx->keys_dev) + offsetof(KeysDev, Nw));
 }
 
+KeysDev* host_keys(scb_ctx* ctx);
+
+// (Re)compile the sliding-window programs of every shared exponent the library owns: the public exponent N of rho^N, lambda,
+// the six CRT exponents, v_p.  Called whenever a key is loaded (device addresses and values may both have changed).
+int rebuild_exponent_programs(scb_ctx* ctx) {
+  ctx->clear_exponent_programs();
+  int rc = SCB_OK;
+  if (ctx->have_paillier_pub && ctx->keys_dev) {
+    const KeysDev* hk = host_keys(ctx);
+    if ((rc = ctx->register_exponent(keys_N_words(ctx), hk->Nw, hk->kN))) return rc;
+  }
+  if (ctx->secret_dev && !ctx->paillier_lambda.empty())
+    if ((rc = ctx->register_exponent(ctx->secret_dev, ctx->paillier_lambda.data(), static_cast<int>(ctx->paillier_lambda.size())))) return rc;
+  if (ctx->have_paillier_crt && ctx->crt_exp_dev) {
+    const int kP = host_keys(ctx)->kP;
+    for (int j = 0; j < 6; j++)
+      if ((rc = ctx->register_exponent(ctx->crt_exp_dev + static_cast<size_t>(j) * kP, ctx->crt_exp_host.data() + static_cast<size_t>(j) * kP, kP))) return rc;
+  }
+  if (ctx->have_dgk_priv && ctx->vp_dev)
+    if ((rc = ctx->register_exponent(ctx->vp_dev, ctx->dgk_vp.data(), static_cast<int>(ctx->dgk_vp.size())))) return rc;
+  return SCB_OK;
+}
+
 KeysDev* host_keys(scb_ctx* ctx) {
   if (ctx->keys_host.size() != sizeof(KeysDev)) ctx->keys_host.assign(sizeof(KeysDev), 0);
   return reinterpret_cast<KeysDev*>(ctx->keys_host.data());
@@ -240,7 +263,9 @@ extern "C" int scb_paillier_set_public(scb_ctx* ctx, const uint32_t* n, int kN) 
   ctx->have_paillier_pub = true;
   ctx->have_paillier_priv = false;
   ctx->have_paillier_crt = false;
-  return upload_keys(ctx);
+  ctx->paillier_lambda.clear();
+  if ((rc = upload_keys(ctx))) return rc;
+  return rebuild_exponent_programs(ctx);
 }
 
 extern "C" int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, int lambda_words, const uint32_t* mu) {
@@ -263,7 +288,7 @@ extern "C" int scb_paillier_set_private(scb_ctx* ctx, const uint32_t* lambda, in
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "upload secret");
   ctx->have_paillier_priv = true;
-  return SCB_OK;
+  return rebuild_exponent_programs(ctx);
 }
 
 extern "C" int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_t* g, const uint32_t* h, const uint32_t* g_neg, int kn,
@@ -337,7 +362,8 @@ extern "C" int scb_dgk_set_private(scb_ctx* ctx, const uint32_t* p, int kp, cons
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "upload v_p");
   ctx->have_dgk_priv = true;
-  return upload_keys(ctx);
+  if ((rc = upload_keys(ctx))) return rc;
+  return rebuild_exponent_programs(ctx);
 }
 
 extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
@@ -345,6 +371,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
   switch (option) {
     case SCB_OPT_PAILLIER_CRT: ctx->use_crt = value != 0; return SCB_OK;
     case SCB_OPT_MODEXP_FP64: ctx->use_f64 = value != 0; return SCB_OK;
+    case SCB_OPT_SLIDING_WINDOWS: ctx->use_sliding = value != 0; return SCB_OK;
     case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }
@@ -454,6 +481,7 @@ extern "C" int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, con
   e = cudaMemcpyAsync(ctx->crt_exp_dev, exps.data(), sizeof(uint32_t) * exps.size(), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "upload crt exponents");
+  ctx->crt_exp_host = exps;
   for (int h = 0; h < 2; h++) {
     ctx->crt_e1_bits[h] = e1_bits[h];
     ctx->crt_P_bits[h] = P_bits[h];
@@ -508,7 +536,8 @@ extern "C" int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, con
   }
   ctx->have_paillier_crt = true;
   ctx->have_paillier_priv = true;
-  return upload_keys(ctx);
+  if ((rc = upload_keys(ctx))) return rc;
+  return rebuild_exponent_programs(ctx);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -206,6 +206,10 @@ class Engine:
         """Large exponentiations on the FP64-pipe multiplier (default) or on the IMAD one; bit-identical results."""
         self._check(self.lib.scb_set_option(self.ctx, nat.OPT_MODEXP_FP64, int(bool(enabled))))
 
+    def set_sliding_windows(self, enabled: bool) -> None:
+        """Sliding-window programs for the library's shared exponents (default) or fixed windows; bit-identical results."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_SLIDING_WINDOWS, int(bool(enabled))))
+
     def set_fixed_base_wide(self, enabled: bool) -> None:
         """16-bit-window fixed-base tables (default) vs 8-bit windows only; applies to tables loaded afterwards."""
         self._check(self.lib.scb_set_option(self.ctx, nat.OPT_FIXED_BASE_WIDE, int(bool(enabled))))

@@ -63,15 +63,18 @@ def test_paillier_crt_and_public_formulas_agree(setup):
     want_dec = [oracle.paillier_decrypt_raw(v) for v in c]
     try:
         for crt in (True, False):
-            for fp64 in (True, False):
+            for fp64, sliding in ((True, True), (True, False), (False, True)):
                 eng.set_paillier_crt(crt)
                 eng.set_modexp_fp64(fp64)
+                eng.set_sliding_windows(sliding)
+                tag = f"crt={crt}, fp64={fp64}, sliding={sliding}"
                 got = eng.paillier_encrypt(ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN))
-                assert limbs_to_ints(got) == want, f"encrypt+randomize, crt={crt}, fp64={fp64}"
-                assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want_dec, f"decrypt, crt={crt}, fp64={fp64}"
+                assert limbs_to_ints(got) == want, f"encrypt+randomize, {tag}"
+                assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(c, eng.kc))) == want_dec, f"decrypt, {tag}"
     finally:
         eng.set_paillier_crt(True)
         eng.set_modexp_fp64(True)
+        eng.set_sliding_windows(True)
 
 
 def test_step1_pieces(setup):
