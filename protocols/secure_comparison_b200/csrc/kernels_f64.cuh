@@ -119,12 +119,11 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
   stage_digits52<L, TPI>(sm_group, r);
   const int ntab = (1 << wbits) - 2;
   const int nmain = (nwin - 1) * (wbits + 1);
+  int pos = 0, wi = nwin - 2;                              // position inside the current window group / index of its window (no divisions in the loop)
 #pragma unroll 1
   for (int step = 0; step < ntab + nmain; step++) {
     if (step >= ntab) {
-      const int k = step - ntab;
-      const int pos = k % (wbits + 1);
-      if (k == 0) {
+      if (step == ntab) {
         const uint32_t win = get_bits(e, ewords, (nwin - 1) * wbits, wbits);
 #pragma unroll
         for (int i = 0; i < L; i++) r[i] = table[static_cast<size_t>(win) * K + t * L + i];
@@ -132,7 +131,6 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
       if (pos < wbits) {
         stage_digits52<L, TPI>(sm_group, r);
       } else {
-        const int wi = nwin - 2 - k / (wbits + 1);
         const uint32_t win = get_bits(e, ewords, wi * wbits, wbits);
         double bv[L];
 #pragma unroll
@@ -141,6 +139,14 @@ __device__ __forceinline__ void group_modexp52(const Modulus52Dev* __restrict__ 
       }
     }
     mmd_rows<L, TPI>(r, nv, np, sm_group, r);
+    if (step >= ntab) {
+      if (pos == wbits) {
+        pos = 0;
+        wi--;
+      } else {
+        pos++;
+      }
+    }
     if (step < ntab) {
 #pragma unroll
       for (int i = 0; i < L; i++) table[static_cast<size_t>(step + 2) * K + t * L + i] = r[i];

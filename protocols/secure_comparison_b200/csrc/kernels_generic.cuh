@@ -80,12 +80,11 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
   stage_digits<L, TPI>(g.sm, r);
   const int ntab = (1 << wbits) - 2;                     // products of the table build: table[v] = table[v-1] * x~, v = 2..2^w-1
   const int nmain = (nwin - 1) * (wbits + 1);            // per remaining window: wbits squarings + 1 window product
+  int pos = 0, wi = nwin - 2;                              // position inside the current window group / index of its window (no divisions in the loop)
 #pragma unroll 1
   for (int step = 0; step < ntab + nmain; step++) {
     if (step >= ntab) {
-      const int k = step - ntab;
-      const int pos = k % (wbits + 1);
-      if (k == 0) {
+      if (step == ntab) {
         // the table is complete (each lane wrote, and now reads, only its own digits): start from the top window
         const uint32_t win = get_bits(e, ewords, (nwin - 1) * wbits, wbits);
 #pragma unroll
@@ -94,7 +93,6 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
       if (pos < wbits) {
         stage_digits<L, TPI>(g.sm, r);                   // squaring: the value is its own b operand
       } else {
-        const int wi = nwin - 2 - k / (wbits + 1);
         const uint32_t win = get_bits(e, ewords, wi * wbits, wbits);
         uint32_t bv[L];
 #pragma unroll
@@ -103,6 +101,14 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
       }
     }
     mm_rows<L, TPI>(r, nv, np, g.sm, r);
+    if (step >= ntab) {
+      if (pos == wbits) {
+        pos = 0;
+        wi--;
+      } else {
+        pos++;
+      }
+    }
     if (step < ntab) {
 #pragma unroll
       for (int i = 0; i < L; i++) table[static_cast<size_t>(step + 2) * K + t * L + i] = r[i];
