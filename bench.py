@@ -53,8 +53,8 @@ MAC_PER_COMPARISON_L16 = 567e6      # reference-faithful operation list of one i
 MAC_PER_MODEXP_4096_2048 = 81.91e6  # one rho^N mod N^2 (k = 128 limbs, 2048-bit exponent)
 # fixed (x, y) pairs of the reference's tests (test_secure_comparison.py:27-37), non-negative ones
 FIXED_PAIRS = [(0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7804), (8668, 9015), (23, 42), (42, 23), (7, 7), (0, 0)]
-# ncu --set full of k_modexp52<10,8> at B = 32768 (profiles/r01p_ncu_k_modexp52_10x8.txt): dram read + write bytes per launch
-NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (4.588519e9 + 1.427151e9) / 32768
+# ncu --set full of k_modexp52<10,8> at B = 32768 (profiles/r01y_ncu_k_modexp52_10x8_final.txt): dram read + write bytes per launch
+NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (2.916283e9 + 1.426988e9) / 32768
 
 
 def _measured_hbm_gbs() -> float:
@@ -306,10 +306,11 @@ def run_ours(args):
                        "pct_of_peak refers to; the IMAD microbenchmark on this pool sustains 8.6 TMAC/s, profiles/r01_imad_microbench2.jsonl)",
         "frac_of_measured_microbench_peak": round(achieved * 1e12 / INT_PEAK_MEASURED_MAC_PER_S, 4),
         "fp64_pipe_frac": round(fp64_ops / (k1_ms * 1e-3) / (148 * 64 * 1.965e9), 4) if (fp64_engine and k1_ms) else None,
-        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 59 %, "
-                          "ALU pipe 47 %, issue slots 57 % (profiles/r01p_ncu_k_modexp52_10x8.txt); a pure DFMA stream sustains 54.5/clk/SM, mixed 1:1 with "
+        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 62 %, "
+                          "ALU pipe 50 %, issue slots 60 % (profiles/r01y_ncu_k_modexp52_10x8_final.txt); a pure DFMA stream sustains 54.5/clk/SM, mixed 1:1 with "
                           "integer adds 46.7 (profiles/r01_fp64_issue_microbench.jsonl)",
-        "imad_engine_reference": "same launch on the IMAD engine: 833 ms at B=65536 = 6.45 TMAC/s algorithmic, fmaheavy pipe 84-87 % busy (profiles/r01e_ncu_k_step1.txt)",
+        "imad_engine_reference": "same launch on the IMAD engine: 833 ms at B=65536 = 6.45 TMAC/s algorithmic, fmaheavy pipe 84-87 % busy "
+                                 "(profiles/r01e_ncu_k_step1.txt, profiles/r01s_ncu_k_modexp_imad_18x4.txt)",
         "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
         "traffic_note": "dram bytes per launch scaled from an ncu capture (window tables of the ~9,500 resident groups exceed L2): "
                         "tens of GB/s, non-binding next to hbm_gbs = 6,550",
