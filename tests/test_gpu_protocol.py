@@ -152,3 +152,36 @@ def test_error_contract():
         Initiator(l).scheme_paillier
     with pytest.raises(ValueError):
         KeyHolder(l).scheme_dgk
+
+
+@pytest.mark.parametrize("key_spec,B", [((2048, 2048, 160, 16), 4096), ((2048, 2048, 160, 32), 1024), ((4096, 3072, 160, 64), 128)],
+                         ids=["config1-l16", "config2-l32", "config3-p4096-d3072-l64"])
+def test_ciphertexts_match_oracle_at_scale(key_spec, B):
+    """BASELINE configs[1..3] key sizes and bit lengths: EVERY message of the interactive flow bit-identical to the CPU
+    oracle on batches of 4,096 / 1,024 / 128 comparisons (the oracle runs on all host cores); the full-size batches of
+    bench.py are covered by the decrypted-bit gate there."""
+    from helpers import oracle_transcripts_parallel
+    l = key_spec[3]
+    paillier, dgk = make_schemes(*key_spec)
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    rng = random.Random(65536)
+    pairs = draw_inputs(rng, B, l)
+    N = paillier.public_key.n
+    # input ciphertexts are made on the GPU (any valid ciphertext of x / y will do; CPython would need minutes for 3,072 of them)
+    plain = ints_to_limbs([v % N for pair in pairs for v in pair], eng.kN)
+    rho_in = ints_to_limbs([rng.randrange(1, N) for _ in range(2 * B)], eng.kN)
+    enc = limbs_to_ints(eng.paillier_encrypt(plain, rho_in))
+    cases = [{"x": x, "y": y, "nonces": draw_nonces(rng, paillier, dgk, l), "x_enc": enc[2 * i], "y_enc": enc[2 * i + 1]}
+             for i, (x, y) in enumerate(pairs)]
+    want = oracle_transcripts_parallel(key_spec, l, cases)
+    arr = pack_case_arrays(cases, l, eng.kN, eng.kn, eng.rand_words, eng.rb_words)
+    out = run_fused(eng, paillier, dgk, l, arr, interactive=True)
+    assert limbs_to_ints(out["z_enc"]) == [t[0] for t in want]
+    assert limbs_to_ints(out["z"]) == [t[1] for t in want]
+    assert limbs_to_ints(out["db_enc"].reshape(B * (l + 1), -1)) == [v for t in want for v in t[2]]
+    assert limbs_to_ints(out["c_enc"].reshape(B * (l + 1), -1)) == [v for t in want for v in t[3]]
+    assert out["delta_b"].tolist() == [t[4] for t in want]
+    assert limbs_to_ints(out["enc3"].reshape(B * 3, -1)) == [v for t in want for v in t[5]]
+    assert limbs_to_ints(out["result"]) == [t[6] for t in want]
+    assert limbs_to_ints(out["bit_raw"]) == [int(x <= y) for x, y in pairs]
