@@ -181,3 +181,41 @@ def test_step4_without_blinding_and_with(setup):
     got = eng.initiator_step4(DB, R, DA, RB, np.array(perm, dtype=np.uint8), None, l)
     want_i = [oracle.step_4i(row, e, p) for row, e, p in zip(want, rb, perm)]
     assert limbs_to_ints(got.reshape(B * (l + 1), -1)) == [v for row in want_i for v in row], "step 4i"
+
+
+def test_empty_and_tiny_batches(setup):
+    """B = 0 is a no-op for every phase (shapes preserved); B = 1, 2, 3 agree with the oracle (ragged warps)."""
+    paillier, dgk, l, eng, oracle, rng = setup
+    kN, kc, kn = eng.kN, eng.kc, eng.kn
+    z0 = np.zeros((0, kN), np.uint32)
+    assert eng.paillier_encrypt(z0).shape == (0, kc)
+    assert eng.paillier_decrypt(np.zeros((0, kc), np.uint32)).shape == (0, kN)
+    assert eng.initiator_step1(np.zeros((0, kc), np.uint32), np.zeros((0, kc), np.uint32), z0, None, l).shape == (0, kc)
+    assert eng.keyholder_step4ab(z0, l, None).shape == (0, l + 1, kn)
+    assert eng.initiator_step4(np.zeros((0, l + 1, kn), np.uint32), z0, np.zeros(0, np.uint8), None, None, None, l).shape == (0, l + 1, kn)
+    db, enc3 = eng.keyholder_step4j_5(np.zeros((0, l + 1, kn), np.uint32), z0, None, l)
+    assert db.shape == (0,) and enc3.shape == (0, 3, kc)
+    assert eng.initiator_step6_7(np.zeros((0, 3, kc), np.uint32), z0, np.zeros(0, np.uint8), l).shape == (0, kc)
+    assert eng.dgk_is_zero(np.zeros((0, kn), np.uint32)).shape == (0,)
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    for B in (1, 2, 3):
+        m = [rng.randrange(N) for _ in range(B)]
+        rho = [rng.randrange(1, N) for _ in range(B)]
+        got = eng.paillier_encrypt(ints_to_limbs(m, kN), ints_to_limbs(rho, kN))
+        assert limbs_to_ints(got) == [(1 + v * N) * pow(r, N, N2) % N2 for v, r in zip(m, rho)]
+        assert limbs_to_ints(eng.paillier_decrypt(got)) == m
+
+
+def test_plaintexts_beyond_n_reduce_like_the_reference(setup):
+    """test_modulo_n_squared (test_secure_comparison.py:166-182): unsafe_encrypt of a plaintext >= N is (1 + m N) mod N^2,
+    and step_1 reduces mod N^2 whatever the magnitude of its inputs (y_enc = N^2 - 2, x_enc = enc(0))."""
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    top = (1 << (32 * eng.kN)) - 1                                   # largest value the [.., kN] plaintext layout can carry
+    m = [N, N + 5, top, (1 << l) + N - 1]
+    assert limbs_to_ints(eng.paillier_encrypt(ints_to_limbs(m, eng.kN))) == [(1 + v * N) % N2 for v in m]
+    x_enc, y_enc, r = 1, N2 - 2, N - 1                               # enc(0) = 1
+    got = limbs_to_ints(eng.initiator_step1(ints_to_limbs([x_enc], eng.kc), ints_to_limbs([y_enc], eng.kc), ints_to_limbs([r], eng.kN), None, l))
+    assert got == [oracle.step_1(x_enc, y_enc, l, r)]
+    y = oracle.paillier_decrypt_raw(y_enc)
+    assert limbs_to_ints(eng.paillier_decrypt(ints_to_limbs(got, eng.kc))) == [(y - 0 + (1 << l) + r) % N]
