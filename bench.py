@@ -325,6 +325,30 @@ def run_ours(args):
         "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
     }
 
+    # ---- the same pass with the exponentiations on the IMAD engine (the integer-pipe design of the north star; identical
+    #      outputs): one warm-up pass, one timed pass, results compared bit for bit with the FP64-engine pass
+    ref_res = d_res.clone()
+    eng.set_modexp_fp64(False)
+    step_device()
+    eng.sync()
+    with torch.cuda.stream(stream):
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record(stream)
+        step_device()
+        i1.record(stream)
+    eng.sync()
+    imad_ms = i0.elapsed_time(i1)
+    imad_same = bool(torch.equal(ref_res, d_res))
+    eng.set_modexp_fp64(True)
+    if world > 1:
+        t = torch.tensor([imad_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        imad_ms = float(t.item())
+    imad_engine = {"value": round(world * B / (imad_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(imad_ms, 3),
+                   "bit_identical_to_fp64_engine": imad_same,
+                   "note": "SCB_OPT_MODEXP_FP64 = 0: every exponentiation on the IMAD.WIDE engine (ncu: fmaheavy pipe 87 % busy, "
+                           "profiles/r01s_ncu_k_modexp_imad_18x4.txt)"}
+
     # ---- second half of the BASELINE metric: 2048-bit modexp/s (full-length per-element exponents, modulus = DGK n),
     #      device resident, k_modexp<18,4>, SURVEY 8d unit = 20.56 M MAC per modexp
     MB = B
@@ -405,7 +429,7 @@ def run_ours(args):
                        "sharding": "contiguous block of the global batch per rank, no data-path collective"},
             "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "modexp_2048": modexp_2048,
+            "modexp_2048": modexp_2048, "imad_engine": imad_engine,
             "modexp_4096_per_s": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
         print(json.dumps(line), flush=True)

@@ -76,6 +76,9 @@ struct scb_ctx {
   std::map<const uint32_t*, ExpProgram> exp_programs;
   bool use_sliding = true;
   int register_exponent(const uint32_t* dev_words, const uint32_t* host_words, int nwords);
+  // program of a shared exponent (nullptr / 0 when none is registered or sliding windows are switched off); *wbits is
+  // raised when the program's table (2^(w-1) entries) needs more scratch than the fixed-window table
+  const uint16_t* find_program(const uint32_t* dev_words, int* nprog, int* pw, int* wbits) const;
   void clear_exponent_programs();
   std::vector<uint32_t> crt_exp_host;
 

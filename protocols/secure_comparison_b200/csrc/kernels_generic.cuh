@@ -123,6 +123,82 @@ __device__ __forceinline__ void group_modexp(const Grp<L, TPI>& g, uint32_t* acc
   for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
 }
 
+// acc = x~^e for a SHARED exponent compiled on the host into a sliding-window program (scb_ctx::register_exponent; format and
+// rationale: group_modexp52_prog in kernels_f64.cuh).  table[i] = x~^(2i+1), i < 2^(pw-1).
+template <int L, int TPI>
+__device__ __forceinline__ void group_modexp_prog(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* xm, const uint16_t* __restrict__ prog,
+                                                  int nprog, int pw, uint32_t* table) {
+  constexpr int K = Geo<L, TPI>::K;
+  const int t = g.t;
+  const int T = 1 << (pw - 1);
+  uint32_t r[L], nv[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) nv[i] = g.m->n[t * L + i];
+  const uint32_t np = g.m->np;
+#pragma unroll
+  for (int i = 0; i < L; i++) r[i] = xm[t * L + i];
+#pragma unroll
+  for (int i = 0; i < L; i++) table[t * L + i] = r[i];
+  const uint32_t idx0 = __ldg(prog);
+  int phase = 0, ti = 1, pe = 1, sq_left = 0;
+  uint32_t cur_idx = 0xFF;
+  bool need_mul = false;
+#pragma unroll 1
+  for (;;) {
+    if (phase == 0) {
+      stage_digits<L, TPI>(g.sm, r);                             // x~ * x~
+    } else if (phase == 2) {
+      if (sq_left == 0 && !need_mul) {
+        if (pe >= nprog) break;
+        const uint32_t e = __ldg(prog + pe++);
+        sq_left = static_cast<int>(e >> 8);
+        cur_idx = e & 0xFFu;
+        need_mul = cur_idx != 0xFFu;
+        if (sq_left == 0 && !need_mul) continue;
+      }
+      if (sq_left > 0) {
+        stage_digits<L, TPI>(g.sm, r);                           // squaring
+        sq_left--;
+      } else {
+        uint32_t bv[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) bv[i] = table[static_cast<size_t>(cur_idx) * K + t * L + i];
+        stage_digits<L, TPI>(g.sm, bv);                          // window product
+        need_mul = false;
+      }
+    }                                                            // phase 1: x~^2 is still staged
+    mm_rows<L, TPI>(r, nv, np, g.sm, r);
+    if (phase == 0) {
+      stage_digits<L, TPI>(g.sm, r);                             // x~^2 stays staged for the whole table build
+#pragma unroll
+      for (int i = 0; i < L; i++) r[i] = table[t * L + i];       // back to x~
+      phase = 1;
+    } else if (phase == 1) {
+#pragma unroll
+      for (int i = 0; i < L; i++) table[static_cast<size_t>(ti) * K + t * L + i] = r[i];
+      ti++;
+    }
+    if (phase == 1 && ti == T) {
+#pragma unroll
+      for (int i = 0; i < L; i++) r[i] = table[static_cast<size_t>(idx0) * K + t * L + i];
+      phase = 2;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < L; i++) acc[t * L + i] = r[i];
+}
+
+// one entry point for both loops: the program when the launch has one, fixed windows otherwise (launch-uniform choice)
+template <int L, int TPI>
+__device__ __forceinline__ void group_modexp_any(const Grp<L, TPI>& g, uint32_t* acc, const uint32_t* xm, const uint32_t* __restrict__ e,
+                                                 int ewords, int ebits, int wbits, uint32_t* table, const uint16_t* __restrict__ prog,
+                                                 int nprog, int pw) {
+  if (prog != nullptr)
+    group_modexp_prog(g, acc, xm, prog, nprog, pw, table);
+  else
+    group_modexp(g, acc, xm, e, ewords, ebits, wbits, table);
+}
+
 // dst = x~ (Montgomery form, lazy, < 4n) of the value x stored in `kw` words at `words`; x may be up to twice
 // as wide as the modulus (x < 2^(58K)): x = lo + hi*R with K-digit halves, x*R = mm(lo, R^2) + mm(hi, R^3).
 // Used for c mod p^2 / rho mod p in the KeyHolder's CRT paths and c mod p in is_zero.  The branch is on
@@ -151,7 +227,7 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp,
          int ewords, size_t exp_stride, int ebits, int wbits, uint32_t* scratch, const uint32_t* __restrict__ mul_in,
-         uint32_t* __restrict__ out, int kout, size_t B, unsigned long long* queue) {
+         uint32_t* __restrict__ out, int kout, size_t B, unsigned long long* queue, const uint16_t* __restrict__ prog, int nprog, int pw) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -165,7 +241,7 @@ k_modexp(const ModulusDev* __restrict__ m, const uint32_t* __restrict__ base, in
   bool active;
   while (GI::next(queue, B, inst, active)) {
     load_mont(g, X, TMP, base + inst * kbase, kbase);            // x~ = x*R (reduces double-width bases)
-    group_modexp(g, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table);
+    group_modexp_any(g, ACC, X, exp + inst * exp_stride, ewords, ebits, wbits, table, prog, nprog, pw);
     if (mul_in != nullptr) {
       words_to_digits(g, TMP, mul_in + inst * kout, kout);
       mm<L, TPI>(m, g.sm, TMP, TMP, m->r2);

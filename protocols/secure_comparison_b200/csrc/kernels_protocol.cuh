@@ -374,7 +374,7 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ plain,
                    const uint32_t* __restrict__ rho, const uint32_t* __restrict__ rho_pow, int ebits, int wbits, uint32_t* scratch,
-                   uint32_t* __restrict__ out, size_t M, unsigned long long* queue) {
+                   uint32_t* __restrict__ out, size_t M, unsigned long long* queue, const uint16_t* __restrict__ prog, int nprog, int pw) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -391,7 +391,7 @@ k_paillier_encrypt(const ModulusDev* __restrict__ m, const KeysDev* __restrict__
     if (rho != nullptr) {
       words_to_digits(g, TMP, rho + i * kN, kN);
       mm<L, TPI>(m, g.sm, X, TMP, m->r2);
-      group_modexp(g, ACC, X, keys->Nw, kN, ebits, wbits, table);
+      group_modexp_any(g, ACC, X, keys->Nw, kN, ebits, wbits, table, prog, nprog, pw);
       group_paillier_encode(g, keys, TMP, plain + i * kN, kN);
       mm<L, TPI>(m, g.sm, ACC, ACC, TMP);
     } else {
@@ -413,7 +413,7 @@ template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ y, const uint32_t* xinv,
         const uint32_t* __restrict__ r, const uint32_t* __restrict__ rho, const uint32_t* __restrict__ rho_pow, int l, int ebits, int wbits,
-        uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue) {
+        uint32_t* scratch, uint32_t* __restrict__ out, size_t B, unsigned long long* queue, const uint16_t* __restrict__ prog, int nprog, int pw) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -443,7 +443,7 @@ k_step1(const ModulusDev* __restrict__ m, const KeysDev* __restrict__ keys, cons
       copy_digits(g, Z, TMP);
       words_to_digits(g, TMP, rho + i * kN, kN);
       mm<L, TPI>(m, g.sm, X, TMP, m->r2);
-      group_modexp(g, ACC, X, keys->Nw, kN, ebits, wbits, table);
+      group_modexp_any(g, ACC, X, keys->Nw, kN, ebits, wbits, table, prog, nprog, pw);
       mm<L, TPI>(m, g.sm, TMP, ACC, Z);
     } else if (rho_pow != nullptr) {                  // rho^N already computed (FP64 engine): [B][2kN] words
       words_to_digits(g, X, rho_pow + i * kc, kc);
@@ -778,7 +778,8 @@ static __global__ void k_flag_is_one(const uint32_t* __restrict__ x, int k, uint
 template <int L, int TPI>
 __global__ void SCB_GROUP_BOUNDS(L)
 k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ keys, const uint32_t* __restrict__ c, const uint32_t* __restrict__ vp,
-              int vp_words, int vp_bits, int wbits, uint32_t* scratch, uint8_t* __restrict__ flags, size_t M, unsigned long long* queue) {
+              int vp_words, int vp_bits, int wbits, uint32_t* scratch, uint8_t* __restrict__ flags, size_t M, unsigned long long* queue,
+              const uint16_t* __restrict__ prog, int nprog, int pw) {
   extern __shared__ uint32_t smem[];
   using GI = GroupIndex<L, TPI>;
   constexpr int K = Geo<L, TPI>::K;
@@ -793,7 +794,7 @@ k_dgk_is_zero(const ModulusDev* __restrict__ mp, const KeysDev* __restrict__ key
   bool active;
   while (GI::next(queue, M, i, active)) {
     load_mont(g, X, TMP, c + i * kn, kn);                        // (c mod p)~ from the double-width c
-    group_modexp(g, ACC, X, vp, vp_words, vp_bits, wbits, table);
+    group_modexp_any(g, ACC, X, vp, vp_words, vp_bits, wbits, table, prog, nprog, pw);
     mm<L, TPI>(mp, g.sm, TMP, ACC, mp->unit);
     stage_from(g, TMP);
     canonicalize_staged(g);

@@ -179,6 +179,18 @@ int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_w
   return SCB_OK;
 }
 
+const uint16_t* scb_ctx::find_program(const uint32_t* dev_words, int* nprog, int* pw, int* wbits) const {
+  *nprog = 0;
+  *pw = 0;
+  if (!use_sliding) return nullptr;
+  auto it = exp_programs.find(dev_words);
+  if (it == exp_programs.end()) return nullptr;
+  *nprog = it->second.n;
+  *pw = it->second.w;
+  if (wbits && it->second.w - 1 > *wbits) *wbits = it->second.w - 1;
+  return it->second.dev;
+}
+
 void scb_ctx::clear_exponent_programs() {
   for (auto& kv : exp_programs) cudaFree(kv.second.dev);
   exp_programs.clear();
@@ -376,7 +388,9 @@ template <int L, int TPI>
 int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, int kbase, const uint32_t* exp, int ewords, size_t estride, int ebits,
                   const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   using G = Geo<L, TPI>;
-  const int wbits = window_bits_for(ebits);
+  int wbits = window_bits_for(ebits);
+  int nprog = 0, pw = 0;
+  const uint16_t* prog = estride == 0 ? ctx->find_program(exp, &nprog, &pw, &wbits) : nullptr;
   const size_t smem = sizeof(uint32_t) * G::WARP_SMEM_WORDS * WARPS_PER_BLOCK;
   const int gpb = GroupIndex<L, TPI>::GROUPS_PER_BLOCK;
   int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_modexp<L, TPI>), smem, B, gpb);
@@ -386,7 +400,7 @@ int launch_modexp(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, in
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_modexp<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev, base, kbase, exp, ewords, estride, ebits, wbits,
-                                                               static_cast<uint32_t*>(scratch), mul_in, out, kout, B, queue);
+                                                               static_cast<uint32_t*>(scratch), mul_in, out, kout, B, queue, prog, nprog, pw);
   char label[64];
   snprintf(label, sizeof(label), "k_modexp<%d,%d>[e=%d]", L, TPI, ebits);   // profile label: geometry and exponent length
   return ctx->launched(label);
@@ -398,17 +412,8 @@ int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, 
   using G = Geo52<L, TPI>;
   int wbits = window_bits_for(ebits);
   // shared exponent with a registered sliding-window program?
-  const uint16_t* prog = nullptr;
   int nprog = 0, pw = 0;
-  if (estride == 0 && ctx->use_sliding) {
-    auto it = ctx->exp_programs.find(exp);
-    if (it != ctx->exp_programs.end()) {
-      prog = it->second.dev;
-      nprog = it->second.n;
-      pw = it->second.w;
-      if (pw - 1 > wbits) wbits = pw - 1;          // scratch: the program's table has 2^(pw-1) entries
-    }
-  }
+  const uint16_t* prog = estride == 0 ? ctx->find_program(exp, &nprog, &pw, &wbits) : nullptr;
   size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
   // tuning aid: SCB_F64_EXTRA_SMEM=<bytes> pads the dynamic shared memory to lower the number of resident blocks
   static const size_t extra_smem = getenv("SCB_F64_EXTRA_SMEM") ? static_cast<size_t>(atol(getenv("SCB_F64_EXTRA_SMEM"))) : 0;

@@ -572,15 +572,17 @@ int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32
     rho_pow = pw;
     rho = nullptr;
   }
+  int wb = wbits, nprog = 0, pw = 0;
+  const uint16_t* prog = ctx->find_program(keys_N_words(ctx), &nprog, &pw, &wb);    // IMAD engine: sliding-window program of N
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_step1<L, TPI>), C::SMEM, B, C::GPB);
   const size_t groups = static_cast<size_t>(grid) * C::GPB;
   void* scratch = nullptr;
-  rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * (modexp_scratch_words<L, TPI>(wbits) + C::K), &scratch);
+  rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * (modexp_scratch_words<L, TPI>(wb) + C::K), &scratch);
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_step1<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, y, xinv, r, rho, rho_pow, l, ebits, wbits,
-                                                                 static_cast<uint32_t*>(scratch), out, B, queue);
+  k_step1<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, y, xinv, r, rho, rho_pow, l, ebits, wb,
+                                                                 static_cast<uint32_t*>(scratch), out, B, queue, prog, nprog, pw);
   rc = ctx->launched("k_step1");
   if (rc) return rc;
   (void)kN;
@@ -606,15 +608,17 @@ int phase_paillier_encrypt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* 
     rho_pow = pw;
     rho = nullptr;
   }
+  int wb = wbits, nprog = 0, pw = 0;
+  const uint16_t* prog = ctx->find_program(keys_N_words(ctx), &nprog, &pw, &wb);
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_paillier_encrypt<L, TPI>), C::SMEM, M, C::GPB);
   const size_t groups = static_cast<size_t>(grid) * C::GPB;
   void* scratch = nullptr;
-  int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * modexp_scratch_words<L, TPI>(wbits), &scratch);
+  int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * groups * modexp_scratch_words<L, TPI>(wb), &scratch);
   if (rc) return rc;
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
-  k_paillier_encrypt<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, plain, rho, rho_pow, ebits, wbits,
-                                                                            static_cast<uint32_t*>(scratch), out, M, queue);
+  k_paillier_encrypt<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, plain, rho, rho_pow, ebits, wb,
+                                                                            static_cast<uint32_t*>(scratch), out, M, queue, prog, nprog, pw);
   return ctx->launched("k_paillier_encrypt");
 }
 
@@ -686,7 +690,9 @@ template <int L, int TPI>
 int phase_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M) {
   using C = Cfg<L, TPI>;
   const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_P];
-  const int wbits = window_bits_for(ctx->dgk_vp_bits);
+  int wbits = window_bits_for(ctx->dgk_vp_bits);
+  int nprog = 0, pw = 0;
+  const uint16_t* prog = ctx->find_program(ctx->vp_dev, &nprog, &pw, &wbits);
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_dgk_is_zero<L, TPI>), C::SMEM, M, C::GPB);
   void* scratch = nullptr;
   int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * modexp_scratch_words<L, TPI>(wbits), &scratch);
@@ -694,7 +700,7 @@ int phase_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M) {
   unsigned long long* queue = ctx->fresh_queue();
   if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
   k_dgk_is_zero<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, c, ctx->vp_dev, static_cast<int>(ctx->dgk_vp.size()),
-                                                                       ctx->dgk_vp_bits, wbits, static_cast<uint32_t*>(scratch), flags, M, queue);
+                                                                       ctx->dgk_vp_bits, wbits, static_cast<uint32_t*>(scratch), flags, M, queue, prog, nprog, pw);
   return ctx->launched("k_dgk_is_zero");
 }
 
