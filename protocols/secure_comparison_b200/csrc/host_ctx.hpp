@@ -79,6 +79,7 @@ struct scb_ctx {
   // program of a shared exponent (nullptr / 0 when none is registered or sliding windows are switched off); *wbits is
   // raised when the program's table (2^(w-1) entries) needs more scratch than the fixed-window table
   const uint16_t* find_program(const uint32_t* dev_words, int* nprog, int* pw, int* wbits) const;
+  void unregister_exponent(const uint32_t* dev_words);
   void clear_exponent_programs();
   std::vector<uint32_t> crt_exp_host;
 

@@ -191,6 +191,14 @@ const uint16_t* scb_ctx::find_program(const uint32_t* dev_words, int* nprog, int
   return it->second.dev;
 }
 
+void scb_ctx::unregister_exponent(const uint32_t* dev_words) {
+  auto it = exp_programs.find(dev_words);
+  if (it == exp_programs.end()) return;
+  cudaStreamSynchronize(stream);
+  cudaFree(it->second.dev);
+  exp_programs.erase(it);
+}
+
 void scb_ctx::clear_exponent_programs() {
   for (auto& kv : exp_programs) cudaFree(kv.second.dev);
   exp_programs.clear();
@@ -816,11 +824,15 @@ extern "C" int scb_modexp(scb_ctx* ctx, int slot, const uint32_t* base, const ui
   const uint32_t* dmul = st.upload(mul_in, B * k);
   uint32_t* dout = st.reserve<uint32_t>(B * k);
   if (st.rc) return st.rc;
+  // a shared exponent is known on the host here: compile it into a sliding-window program for this call
+  if (exp_shared && (rc = ctx->register_exponent(dexp, exp, exp_words))) return rc;
   rc = scb_modexp_dev(ctx, slot, dbase, dexp, exp_words, exp_shared, exp_bits, dmul, dout, B);
-  if (rc) return rc;
-  st.download(out, dout, B * k);
-  if (st.rc) return st.rc;
-  return scb_sync(ctx);
+  if (rc == SCB_OK) {
+    st.download(out, dout, B * k);
+    rc = st.rc ? st.rc : scb_sync(ctx);
+  }
+  if (exp_shared) ctx->unregister_exponent(dexp);
+  return rc;
 }
 
 extern "C" int scb_modmul(scb_ctx* ctx, int slot, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t B) {

@@ -159,3 +159,30 @@ def test_fp64_engine_carry_resolution_rare_paths(eng):
         assert value < 1 << (52 * K), "test case overflows the representation"
         assert all(d <= M52 for d in digits)
         assert sum(d << (52 * i) for i, d in enumerate(digits)) == value
+
+
+@pytest.mark.parametrize("fp64", [True, False], ids=["fp64", "imad"])
+@pytest.mark.parametrize("sliding", [True, False], ids=["sliding", "fixed"])
+def test_shared_exponent_programs_on_crafted_exponents(eng, fp64, sliding):
+    """The host-pointer modexp compiles a SHARED exponent into a sliding-window program: exponents with zero runs longer
+    than one program entry can hold (255 squarings), a single set bit, all ones, trailing zeros, and short exponents that
+    stay on the fixed-window loop -- all against Python's pow, on both engines."""
+    rng = random.Random(77)
+    bits = 2048
+    n = rand_modulus(rng, bits)
+    k = eng.load_modulus(SLOT, n)
+    B = 24
+    bases = [rng.randrange(n) for _ in range(B)]
+    bases[:3] = [0, 1, n - 1]
+    exps = [(1 << 1500) + 1, 1 << 2047, (1 << 2048) - 1, ((rng.getrandbits(700) | 1) << 1200) | rng.getrandbits(500) | (1 << 499),
+            rng.getrandbits(2048) << 0 | (1 << 2047), (rng.getrandbits(1000) | (1 << 999)) << 600, (1 << 63) | 5, 12345, 1 << 64, 3]
+    eng.set_modexp_fp64(fp64)
+    eng.set_sliding_windows(sliding)
+    try:
+        for e in exps:
+            ew = max(1, (e.bit_length() + 31) // 32)
+            out = eng.modexp(SLOT, ints_to_limbs(bases, k), ints_to_limbs([e], ew)[0], e.bit_length())
+            assert limbs_to_ints(out) == [pow(b, e, n) for b in bases], f"exponent of {e.bit_length()} bits"
+    finally:
+        eng.set_modexp_fp64(True)
+        eng.set_sliding_windows(True)
