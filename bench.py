@@ -295,7 +295,8 @@ def run_ours(args):
     nprod = ebits_N + -(-ebits_N // 6) + 64                 # squarings + 6-bit-window products + table (2,455 at 2048 bits)
     fp64_ops = B * nprod * (2 * K52 * K52 * 3 + K52 * 4)    # DFMA/DADD thread-instructions of one launch
     roofline = {
-        "bound": "multiplier pipes, not hbm and not tensor: " + (
+        "bound": "int-pipe",
+        "bound_detail": "multiplier pipes, not hbm and not tensor (north star: integer-multiply roofline): " + (
             "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; throughput-limited on the DFMA + IADD3 instruction mix)"
             if fp64_engine else "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy)"),
         "kernel": k1_name, "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,

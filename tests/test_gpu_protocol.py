@@ -185,3 +185,38 @@ def test_ciphertexts_match_oracle_at_scale(key_spec, B):
     assert limbs_to_ints(out["enc3"].reshape(B * 3, -1)) == [v for t in want for v in t[5]]
     assert limbs_to_ints(out["result"]) == [t[6] for t in want]
     assert limbs_to_ints(out["bit_raw"]) == [int(x <= y) for x, y in pairs]
+
+
+@pytest.mark.parametrize("x,y", [(23, 42), (42, 23), (7, 7), (-400, -383)])
+def test_readme_example_call_sequence(x, y):
+    """BASELINE configs[0]: the README's step-by-step flow (README.md:117-141), call for call and with the README's argument
+    lists (no scheme argument where the reference has none), scalar scheme ciphertext OBJECTS as inputs, l = 16,
+    Paillier-2048 / DGK-2048 (v = 160): x = 23, y = 42 -> 1."""
+    from oracle.schemes import PaillierCiphertext
+    l = 16
+    scheme_paillier, scheme_dgk = make_schemes(2048, 2048, 160, l)
+    reset_engines()
+    x_enc = scheme_paillier.unsafe_encrypt(x)
+    y_enc = scheme_paillier.unsafe_encrypt(y)
+    alice = Initiator(l)
+    bob = KeyHolder(l, scheme_paillier=scheme_paillier, scheme_dgk=scheme_dgk)
+    z_enc, r = alice.step_1(x_enc, y_enc, l, scheme_paillier)
+    z, beta = bob.step_2(z_enc, l, scheme_paillier)
+    alpha = alice.step_3(r, l)
+    d_enc = bob.step_4a(z, scheme_dgk, scheme_paillier, l)
+    beta_is_enc = bob.step_4b(beta, l, scheme_dgk)
+    d_enc = alice.step_4c(d_enc, r, scheme_dgk, scheme_paillier)
+    alpha_is_xor_beta_is_enc = alice.step_4d(alpha, beta_is_enc)
+    w_is_enc, alpha_tilde = alice.step_4e(r, alpha, alpha_is_xor_beta_is_enc, d_enc, scheme_paillier)
+    w_is_enc = alice.step_4f(w_is_enc)
+    s, delta_a = alice.step_4g()
+    c_is_enc = alice.step_4h(s, alpha, alpha_tilde, d_enc, beta_is_enc, w_is_enc, delta_a, scheme_dgk)
+    c_is_enc = alice.step_4i(c_is_enc, scheme_dgk)
+    delta_b = bob.step_4j(c_is_enc, scheme_dgk)
+    zeta_1_enc, zeta_2_enc, delta_b_enc = bob.step_5(z, l, delta_b, scheme_paillier)
+    beta_lt_alpha_enc = alice.step_6(delta_a, delta_b_enc)
+    x_leq_y_enc = alice.step_7(zeta_1_enc, zeta_2_enc, r, l, beta_lt_alpha_enc, scheme_paillier)
+    raw = limbs_to_ints(x_leq_y_enc)[0]
+    x_leq_y = scheme_paillier.decrypt(PaillierCiphertext(raw, scheme_paillier))       # the scheme's own decrypt, as in the README
+    assert x_leq_y == int(x <= y)
+    assert limbs_to_ints(get_engine(scheme_paillier).paillier_decrypt(x_leq_y_enc)) == [int(x <= y)]
