@@ -76,7 +76,7 @@ def parse_args():
     ap.add_argument("--l", type=int, default=16)
     ap.add_argument("--paillier-bits", type=int, default=2048)
     ap.add_argument("--dgk-bits", type=int, default=2048)
-    ap.add_argument("--cpu-per-core", type=int, default=40, help="comparisons per host core in the CPU sample")
+    ap.add_argument("--cpu-per-core", type=int, default=128, help="comparisons per host core in the CPU sample (~7 s per core at 2048 bits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -416,8 +416,11 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle as the timed CPU port, never on the product path
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_baseline import time_comparisons
-        cpu = time_comparisons(2048, 2048, 160, l, per_core=args.cpu_per_core)
+        from oracle.cpu_baseline import time_comparisons, time_modexp
+        cpu = time_comparisons(args.paillier_bits, args.dgk_bits, 160, l, per_core=args.cpu_per_core)
+        cpu["modexp_2048_per_s_per_core"] = time_modexp(2048, 96)["modexp_per_s_per_core"]     # full-length exponent, mpz_powm, one core
+        cpu["speedup_e2e_vs_all_cores"] = (e2e["value"] / cpu["value"]) if e2e else None
+        cpu["speedup_e2e_vs_one_core"] = (e2e["value"] / cpu["per_core_comparisons_per_s"]) if e2e else None
         cpu = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in cpu.items()}
 
     if rank == 0:
