@@ -114,6 +114,12 @@ int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp
  * normalised 52-bit digits.  Its second-order ripple path is unreachable with random operands, so tests drive it here. */
 int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G);
 
+/* Test hook, host only (no GPU): the sliding-window program the library compiles for a shared exponent.  Returns the number
+ * of entries written (0 = the exponent is below 2^63 and stays on the fixed-window loop), negative on error.
+ * prog[0] = table index of the leading window; prog[i>=1] = (squarings << 8) | table index (0xFF = no product);
+ * table[j] = base^(2j+1), j < 2^(window_bits-1). */
+int scb_debug_compile_exponent(const uint32_t* exp, int exp_words, uint16_t* prog_out, int prog_capacity, int* window_bits);
+
 /* ---- scheme keys ------------------------------------------------------------------------------------
  * Replace the scheme objects the reference threads through every step (tno.mpc.encryption_schemes
  * Paillier / DGK: public_key.{n, n_squared, g} / secret_key.{lambda_, mu}; public_key.{n, g, h, u, t} /

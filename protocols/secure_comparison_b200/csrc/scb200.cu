@@ -113,18 +113,15 @@ int scb_ctx::scratch(int which, size_t bytes, void** out) {
   return SCB_OK;
 }
 
-// Compile a shared exponent into a left-to-right sliding-window program (format: kernels_f64.cuh, group_modexp52_prog)
-// and keep it on the device, keyed by the device address of the exponent words.
-int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_words, int nwords) {
+// Compile an exponent into a left-to-right sliding-window program (format: kernels_f64.cuh, group_modexp52_prog).
+// Pure host code.  Returns an empty program for exponents below 2^63 (they stay on the fixed-window loop).
+static std::vector<uint16_t> compile_exponent_program(const uint32_t* host_words, int nwords, int* w_out) {
+  std::vector<uint16_t> prog;
   int top = -1;
   for (int i = nwords - 1; i >= 0 && top < 0; i--)
     if (host_words[i]) top = i * 32 + 31 - __builtin_clz(host_words[i]);
-  auto it = exp_programs.find(dev_words);
-  if (it != exp_programs.end()) {
-    cudaFree(it->second.dev);
-    exp_programs.erase(it);
-  }
-  if (top < 63) return SCB_OK;                     // short (or zero) exponents stay on the fixed-window loop
+  *w_out = 0;
+  if (top < 63) return prog;
   const int bits = top + 1;
   int w = 2;
   double best = 1e30;
@@ -133,7 +130,6 @@ int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_w
     if (cost < best) { best = cost; w = cand; }
   }
   auto bit = [&](int i) -> int { return (host_words[i >> 5] >> (i & 31)) & 1u; };
-  std::vector<uint16_t> prog;
   int i = top, pending = 0;
   bool first = true;
   auto emit = [&](int nsq, int idx) {
@@ -164,6 +160,31 @@ int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_w
     i = s - 1;
   }
   if (pending > 0) emit(pending, 0xFF);
+  *w_out = w;
+  return prog;
+}
+
+// host-only test hook: the program the library would run for a shared exponent (no GPU involved)
+extern "C" int scb_debug_compile_exponent(const uint32_t* exp, int exp_words, uint16_t* prog_out, int prog_capacity, int* window_bits) {
+  if (!exp || exp_words <= 0 || !prog_out || !window_bits) return SCB_EINVAL;
+  int w = 0;
+  const std::vector<uint16_t> prog = compile_exponent_program(exp, exp_words, &w);
+  *window_bits = w;
+  if (static_cast<int>(prog.size()) > prog_capacity) return SCB_EINVAL;
+  for (size_t i = 0; i < prog.size(); i++) prog_out[i] = prog[i];
+  return static_cast<int>(prog.size());
+}
+
+// Keep the program of a shared exponent on the device, keyed by the device address of the exponent words.
+int scb_ctx::register_exponent(const uint32_t* dev_words, const uint32_t* host_words, int nwords) {
+  auto it = exp_programs.find(dev_words);
+  if (it != exp_programs.end()) {
+    cudaFree(it->second.dev);
+    exp_programs.erase(it);
+  }
+  int w = 0;
+  const std::vector<uint16_t> prog = compile_exponent_program(host_words, nwords, &w);
+  if (prog.empty()) return SCB_OK;                 // short (or zero) exponents stay on the fixed-window loop
   ExpProgram ep;
   ep.n = static_cast<int>(prog.size());
   ep.w = w;
