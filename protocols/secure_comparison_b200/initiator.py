@@ -122,6 +122,20 @@ class Initiator:
         elif differs(self.scheme_dgk, received_dgk):
             raise ValueError("Readily available DGK scheme and received DGK scheme are different.")
 
+    @staticmethod
+    def shuffle(values, perm: Optional[np.ndarray] = None):
+        """Shuffle in random order (initiator.py:212-226).  A plain list is shuffled like the reference does (uniform
+        permutation from ``secrets``); a batch ``[B][n][...]`` array is shuffled independently per comparison along axis 1
+        (``perm``: ``[B][n]``, output position k takes element ``perm[b][k]``)."""
+        if isinstance(values, np.ndarray) and values.ndim >= 2:
+            if perm is None:
+                perm = random_permutations(values.shape[0], values.shape[1])
+            idx = np.asarray(perm, dtype=np.int64).reshape(values.shape[0], values.shape[1], *([1] * (values.ndim - 2)))
+            return np.take_along_axis(values, idx, axis=1)
+        values = list(values)
+        order = random_permutations(1, len(values))[0] if perm is None else np.asarray(perm).reshape(-1)
+        return [values[int(i)] for i in order]
+
     # ------------------------------------------------------------------ steps (static, as in the reference)
     @staticmethod
     def step_1(x_enc, y_enc, l: int, scheme_paillier, r: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:

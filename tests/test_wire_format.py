@@ -40,3 +40,16 @@ def test_schemes_roundtrip_public_parts_only():
     assert hex(dgk.secret_key.p)[2:].encode() not in blob and dgk.secret_key.p.to_bytes(32, "little")[:8] not in blob
     with pytest.raises(ValueError):
         wire.unpack_schemes(blob + b"\0")
+
+
+def test_initiator_shuffle_mirrors_the_reference():
+    """Initiator.shuffle (initiator.py:212-226): a uniform permutation of a list; per-comparison along axis 1 for batches."""
+    from protocols.secure_comparison_b200.initiator import Initiator
+    values = list(range(17))
+    out = Initiator.shuffle(values)
+    assert sorted(out) == values and values == list(range(17))          # input untouched
+    batch = np.arange(2 * 5 * 3).reshape(2, 5, 3)
+    out = Initiator.shuffle(batch, perm=np.array([[4, 3, 2, 1, 0], [0, 1, 2, 3, 4]]))
+    assert np.array_equal(out[0], batch[0, ::-1]) and np.array_equal(out[1], batch[1])
+    out = Initiator.shuffle(batch)
+    assert sorted(out[1, :, 0].tolist()) == batch[1, :, 0].tolist()
