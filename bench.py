@@ -433,9 +433,9 @@ def run_ours(args):
         h = {k: (v.view(np.uint32) if v.dtype == np.int32 else v) for k, v in h.items()}
 
         # the public host-buffer API: LocalPipeline = the five party-phases through the synchronous host-pointer C-ABI calls,
-        # batch split in chunks over two contexts (streams) so that one chunk's PCIe copies overlap another's kernels
+        # batch split in two halves over two contexts (streams) so that one half's PCIe copies overlap the other's kernels
         from protocols.secure_comparison_b200.pipeline import LocalPipeline
-        pipe = LocalPipeline(paillier, dgk, l, device=local, n_contexts=2, chunks=4)
+        pipe = LocalPipeline(paillier, dgk, l, device=local, n_contexts=2, chunks=2)    # best of tools/time_pipeline.py
         res = pipe.arena.empty((B, kc))
 
         pipe.compare(h, res)                      # warm-up: scratch growth, pinned result buffers
@@ -455,7 +455,7 @@ def run_ours(args):
         same = bool(np.array_equal(res, d_res.cpu().numpy().view(np.uint32)))
         e2e = {"value": round(world * B * args.steps / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same,
-               "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 4 chunks, pinned buffers)"}
+               "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 2 chunks, pinned buffers)"}
         pipe.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle as the timed CPU port, never on the product path

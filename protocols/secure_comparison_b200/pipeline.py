@@ -59,7 +59,7 @@ class LocalPipeline:
                 eng.load_paillier(scheme_paillier)
                 eng.load_dgk(scheme_dgk, l)
                 self.engines.append(eng)
-        self.chunks = chunks if chunks is not None else 2 * len(self.engines)
+        self.chunks = chunks if chunks is not None else len(self.engines)      # one chunk per context measured best (tools/time_pipeline.py)
         self.pool = ThreadPoolExecutor(max_workers=len(self.engines))
         self.arena = PinnedArena()
         self._bufs: Dict[tuple, dict] = {}
