@@ -53,3 +53,28 @@ def test_initiator_shuffle_mirrors_the_reference():
     assert np.array_equal(out[0], batch[0, ::-1]) and np.array_equal(out[1], batch[1])
     out = Initiator.shuffle(batch)
     assert sorted(out[1, :, 0].tolist()) == batch[1, :, 0].tolist()
+
+
+def test_in_memory_communicator_round_trip():
+    import asyncio
+    from protocols.secure_comparison_b200 import Communicator, InMemoryCommunicator
+    log = []
+    alice = InMemoryCommunicator(log=log)
+    bob = alice.peer()
+    assert isinstance(alice, Communicator) and isinstance(bob, Communicator)
+
+    async def talk():
+        async def late_send():
+            await asyncio.sleep(0.01)
+            await bob.send("alice", wire.pack(np.arange(6, dtype=np.uint32).reshape(2, 3)), msg_id="m1")
+        task = asyncio.ensure_future(late_send())
+        got = await alice.recv("bob", msg_id="m1")                 # waits for the message
+        await task
+        return got
+
+    got = asyncio.run(talk())
+    assert np.array_equal(wire.unpack(got), np.arange(6, dtype=np.uint32).reshape(2, 3))
+    assert log == [("m1", "bytes", 8 + 8 + 24)]
+    quick = InMemoryCommunicator(timeout_s=0.01)
+    with pytest.raises(KeyError):
+        asyncio.run(quick.recv("nobody", msg_id="missing"))
