@@ -16,22 +16,10 @@ from protocols.secure_comparison_b200 import Initiator, KeyHolder, get_engine, l
 pytestmark = pytest.mark.gpu
 
 
-class DictionaryCommunicator:
-    """In-memory transport keyed by msg_id (mirrors the reference's test double)."""
-
-    def __init__(self, store, log):
-        self.store, self.log = store, log
-
-    async def send(self, party_id, message, msg_id=None):
-        self.log.append((msg_id, type(message).__name__))
-        self.store[msg_id] = message
-
-    async def recv(self, party_id, msg_id=None):
-        for _ in range(20000):
-            if msg_id in self.store:
-                return self.store.pop(msg_id)
-            await asyncio.sleep(0.0005)
-        raise KeyError(msg_id)
+def DictionaryCommunicator(store, log):
+    """The package's loop-back transport on a shared mailbox (the counterpart of the reference's test double)."""
+    from protocols.secure_comparison_b200 import InMemoryCommunicator
+    return InMemoryCommunicator(store, log)
 
 
 @pytest.mark.parametrize("wire_format", [False, True], ids=["arrays", "packed"])
@@ -60,8 +48,8 @@ def test_interactive_batch_matches_oracle(wire_format):
     ts = [oracle.compare(c["x_enc"], c["y_enc"], l, c["nonces"], interactive=True) for c in cases]
     assert limbs_to_ints(result) == [t.result_enc for t in ts]
     assert limbs_to_ints(eng.paillier_decrypt(result)) == [int(x <= y) for x, y in pairs]
-    assert [m for m, _ in log] == ["schemes_session_1", "step_1_session_1", "step_4b_session_1", "step_4i_session_1", "step_5_session_1"]
-    assert all((kind == "bytes") == wire_format for _, kind in log)
+    assert [m for m, _, _ in log] == ["schemes_session_1", "step_1_session_1", "step_4b_session_1", "step_4i_session_1", "step_5_session_1"]
+    assert all((kind == "bytes") == wire_format for _, kind, _ in log)
     assert alice.scheme_paillier.public_key.n == paillier.public_key.n and getattr(alice.scheme_paillier, "secret_key", None) is None
 
 
