@@ -70,6 +70,13 @@ int scb_profile_end(scb_ctx* ctx, char* json_out, size_t json_bytes);
 /* pinned host memory for callers that want DMA-able staging buffers */
 int scb_host_alloc(size_t bytes, void** out);
 int scb_host_free(void* ptr);
+/* Device buffers for callers that keep data resident between *_dev calls (the batched Initiator / KeyHolder drivers hold
+ * r, delta_A and z on the device across the phases of a session).  Copies are enqueued on the context's stream:
+ * scb_sync before reading the destination of a device-to-host copy or reusing the source of a host-to-device copy. */
+int scb_dev_alloc(scb_ctx* ctx, size_t bytes, void** out);
+int scb_dev_free(scb_ctx* ctx, void* ptr);
+int scb_copy_h2d(scb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int scb_copy_d2h(scb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
 /* ---- generic batched primitives -------------------------------------------------------------------
  * Replace tno.mpc.encryption_schemes.utils.pow_mod / mod_inv -> gmpy2.powmod / gmpy2.invert and the
@@ -77,6 +84,13 @@ int scb_host_free(void* ptr);
 
 /* Load an odd modulus of k32 words into a slot (Montgomery constants are derived on the host). */
 int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k32);
+
+/* Declare that the modulus in `square_slot` is the SQUARE of the modulus in `root_slot` (both loaded; checked).  Exponentiations
+ * in square_slot then run in base-root pair form (x = a + b n, three half-size Montgomery passes per product, two per
+ * squaring) with bit-identical results.  The key-loading calls below link N^2 -> N, p^2 -> p and q^2 -> q themselves:
+ * rho^N mod N^2 (initiator.py:109), c^(p-1) mod p^2 and b^p mod p^2 (keyholder.py:126-128, 195).  Loading either slot
+ * again drops the link. */
+int scb_modulus_link_square(scb_ctx* ctx, int square_slot, int root_slot);
 
 /* out[i] = base[i] ^ exp[i] mod n.   base: [B][k32]; exp: [B][exp_words] or, when exp_shared != 0, a
  * single [exp_words] exponent used for every element; exp_bits = number of significant exponent bits
@@ -140,8 +154,11 @@ enum {
   SCB_OPT_FIXED_BASE_WIDE = 2,  /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
   SCB_OPT_SLIDING_WINDOWS = 4,  /* sliding-window programs for the shared exponents the library owns (N, CRT exponents, v_p, lambda) on the
                                    FP64 engine (default 1; 0 = fixed windows everywhere) */
-  SCB_OPT_MODEXP_FP64 = 3       /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
+  SCB_OPT_MODEXP_FP64 = 3,      /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
                                    the IMAD one (default 1; results are bit-identical either way) */
+  SCB_OPT_SQUARE_MODULUS = 5    /* exponentiations modulo a linked square n^2 (N^2, p^2, q^2: scb_modulus_link_square) in base-n pair
+                                   form on the FP64 engine: half the digit products of a plain product mod n^2 (default 1; 0 = treat
+                                   n^2 as an ordinary modulus; results are bit-identical either way) */
 };
 int scb_set_option(scb_ctx* ctx, int option, int value);
 /* DGK public key: n, g, h of kn words; g_neg = the raw ciphertext the scheme produces for plaintext -1

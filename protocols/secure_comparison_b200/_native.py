@@ -18,6 +18,7 @@ OPT_PAILLIER_CRT = 1
 OPT_FIXED_BASE_WIDE = 2
 OPT_MODEXP_FP64 = 3
 OPT_SLIDING_WINDOWS = 4
+OPT_SQUARE_MODULUS = 5
 RNG_BELOW, RNG_BITS, RNG_COINS, RNG_PERMUTATIONS, RNG_BLOCK = 0, 1, 2, 3, 4
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 
@@ -40,7 +41,12 @@ _SIGNATURES = {
     "scb_profile_end": ([_vp, ctypes.c_char_p, ctypes.c_size_t], ctypes.c_int),
     "scb_host_alloc": ([ctypes.c_size_t, ctypes.POINTER(_vp)], ctypes.c_int),
     "scb_host_free": ([_vp], ctypes.c_int),
+    "scb_dev_alloc": ([_vp, ctypes.c_size_t, ctypes.POINTER(_vp)], ctypes.c_int),
+    "scb_dev_free": ([_vp, _vp], ctypes.c_int),
+    "scb_copy_h2d": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_copy_d2h": ([_vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_modulus_load": ([_vp, ctypes.c_int, _vp, ctypes.c_int], ctypes.c_int),
+    "scb_modulus_link_square": ([_vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_modexp": ([_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_modexp_dev": ([_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_modmul": ([_vp, ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),

@@ -10,6 +10,7 @@
 namespace scb {
 struct ModulusDev;
 struct Modulus52Dev;
+struct PairConsts52Dev;
 struct KeysDev;
 }  // namespace scb
 
@@ -23,6 +24,10 @@ struct scb_ctx {
     int K = 0, k32 = 0, bits = 0, K52 = 0;
     bool loaded = false;
     std::vector<uint32_t> words;
+    // this modulus is the SQUARE of the modulus in slot `root_slot` (scb_modulus_link_square): exponentiations run in
+    // base-root pair form on the FP64 engine (kernels_f64_pair.cuh); pair52 = their constants
+    int root_slot = -1;
+    scb::PairConsts52Dev* pair52 = nullptr;
   };
   struct FixedBase {
     uint32_t* table = nullptr;   // [nwin][256][K] Montgomery digits (8-bit windows)
@@ -55,6 +60,7 @@ struct scb_ctx {
   // Paillier CRT form: device exponents [e1p, p, p-1, e1q, q, q-1] (kP words each) and their bit lengths
   bool have_paillier_crt = false, use_crt = true;
   bool use_f64 = true;                // large exponentiations on the FP64 engine (bn52.cuh) instead of the IMAD engine
+  bool use_pair = true;               // exponentiations modulo a linked square n^2 in base-n pair form (half the digit products)
   bool fb_wide = true;                // build 16-bit-window fixed-base tables when memory allows
   uint32_t* crt_exp_dev = nullptr;
   int crt_e1_bits[2] = {0, 0}, crt_P_bits[2] = {0, 0};
@@ -97,6 +103,8 @@ namespace scb {
 int fail(scb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what);
 int config_K_for_bits(int bits);
+// declare slot `square_slot` (already loaded with n^2) to be the square of slot `root_slot` (already loaded with n)
+int link_square_modulus(scb_ctx* ctx, int square_slot, int root_slot);
 int modinv_dev_raw(scb_ctx* ctx, int slot, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t B);
 // out = (mul_in *) base^exp with either engine (FP64 when enabled and the modulus has an FP64 geometry)
 int modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, const uint32_t* exp, int exp_words, size_t exp_stride, int exp_bits,

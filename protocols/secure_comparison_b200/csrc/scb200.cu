@@ -14,6 +14,7 @@
 #include "host_ctx.hpp"
 #include "kernels_generic.cuh"
 #include "kernels_f64.cuh"
+#include "kernels_f64_pair.cuh"
 
 using namespace scb;
 
@@ -263,6 +264,7 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   for (auto& m : ctx->mod) {
     if (m.dev) cudaFree(m.dev);
     if (m.dev52) cudaFree(m.dev52);
+    if (m.pair52) cudaFree(m.pair52);
   }
   for (auto& t : ctx->fb) {
     if (t.table) cudaFree(t.table);
@@ -296,6 +298,40 @@ extern "C" int scb_host_alloc(size_t bytes, void** out) {
   return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? SCB_OK : SCB_ENOMEM;
 }
 extern "C" int scb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SCB_OK : SCB_ECUDA; }
+
+extern "C" int scb_dev_alloc(scb_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return SCB_EINVAL;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scb_dev_alloc)");
+  return SCB_OK;
+}
+extern "C" int scb_dev_free(scb_ctx* ctx, void* ptr) {
+  if (!ctx) return SCB_EINVAL;
+  if (!ptr) return SCB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFree(scb_dev_free)");
+  return SCB_OK;
+}
+extern "C" int scb_copy_h2d(scb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx || (bytes && (!dst_dev || !src_host))) return fail(ctx, SCB_EINVAL, "scb_copy_h2d: null pointer");
+  if (!bytes) return SCB_OK;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D copy");
+  return SCB_OK;
+}
+extern "C" int scb_copy_d2h(scb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx || (bytes && (!dst_host || !src_dev))) return fail(ctx, SCB_EINVAL, "scb_copy_d2h: null pointer");
+  if (!bytes) return SCB_OK;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H copy");
+  return SCB_OK;
+}
 
 // -------------------------------------------------------------------------------------------------
 // modulus constants
@@ -355,6 +391,9 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
   md.bits = bits;
   md.words.assign(n, n + k32);
   md.loaded = true;
+  md.root_slot = -1;                                      // a reloaded modulus is no longer a linked square ...
+  for (auto& other : ctx->mod)
+    if (other.root_slot == slot) other.root_slot = -1;    // ... nor the root of one
   // ---- FP64 engine constants (52-bit digits as doubles): n, n' = -n^-1 mod 2^52, R, R^2, R^3 mod n with R = 2^(52 K52)
   md.K52 = config_K52_for_bits(bits);
   if (md.K52 > 0 && 32 * k32 <= 52 * md.K52) {
@@ -398,6 +437,107 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
   }
   return SCB_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// square moduli: constants of the base-n pair arithmetic (kernels_f64_pair.cuh), derived once per key on the host
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+Words words_mul(const Words& a, const Words& b) {
+  Words r(a.size() + b.size(), 0);
+  for (size_t i = 0; i < a.size(); i++) {
+    uint64_t carry = 0;
+    for (size_t j = 0; j < b.size(); j++) {
+      const uint64_t t = static_cast<uint64_t>(a[i]) * b[j] + r[i + j] + carry;
+      r[i + j] = static_cast<uint32_t>(t);
+      carry = t >> 32;
+    }
+    r[i + b.size()] = static_cast<uint32_t>(carry);
+  }
+  return r;
+}
+
+// a = q * n + r by shift-and-subtract (one-off, 4096..8192-bit values); n has no leading zero WORD requirement
+void words_divmod(const Words& a, const Words& n, Words& q, Words& r) {
+  Words nn(n);
+  nn.push_back(0);
+  r.assign(nn.size(), 0);
+  q.assign(a.size(), 0);
+  for (int bit = words_bits(a) - 1; bit >= 0; bit--) {
+    uint32_t carry = (a[bit >> 5] >> (bit & 31)) & 1u;
+    for (size_t i = 0; i < r.size(); i++) {
+      const uint32_t nc = r[i] >> 31;
+      r[i] = (r[i] << 1) | carry;
+      carry = nc;
+    }
+    if (words_geq(r, nn)) {
+      words_sub(r, nn);
+      q[bit >> 5] |= 1u << (bit & 31);
+    }
+  }
+  r.pop_back();
+}
+
+}  // namespace
+
+int scb::link_square_modulus(scb_ctx* ctx, int square_slot, int root_slot) {
+  if (!ctx) return SCB_EINVAL;
+  if (square_slot < 0 || square_slot >= SCB_MOD_SLOTS || root_slot < 0 || root_slot >= SCB_MOD_SLOTS || square_slot == root_slot)
+    return fail(ctx, SCB_EINVAL, "scb_modulus_link_square: bad slot");
+  scb_ctx::Mod& sq = ctx->mod[square_slot];
+  const scb_ctx::Mod& rt = ctx->mod[root_slot];
+  if (!sq.loaded || !rt.loaded) return fail(ctx, SCB_ESTATE, "scb_modulus_link_square: both moduli must be loaded first");
+  Words n2 = words_mul(rt.words, rt.words);
+  n2.resize(std::max(n2.size(), sq.words.size()), 0);
+  Words have(sq.words);
+  have.resize(n2.size(), 0);
+  if (n2 != have) return fail(ctx, SCB_EINVAL, "scb_modulus_link_square: slot %d does not hold the square of slot %d", square_slot, root_slot);
+  sq.root_slot = -1;
+  if (rt.K52 <= 0 || 2 * rt.K52 > MAXK52) return SCB_OK;      // no FP64 geometry for the root: n^2 stays an ordinary modulus
+  cudaSetDevice(ctx->device);
+  const int K = rt.K52;
+  std::vector<uint8_t> buf(sizeof(PairConsts52Dev), 0);
+  PairConsts52Dev* h = reinterpret_cast<PairConsts52Dev*>(buf.data());
+  h->K = K;
+  h->w = rt.bits - 1;
+  Words n2w(n2);
+  while (n2w.size() > 1 && n2w.back() == 0) n2w.pop_back();
+  n2w.push_back(0);                                            // spare top word for the doubling
+  auto to52 = [&](const Words& x, double* digits) {
+    for (int d = 0; d < K; d++) {
+      const int bit = d * 52, w = bit >> 5, sh = bit & 31;
+      auto word = [&](int i) -> uint64_t { return static_cast<size_t>(i) < x.size() ? x[i] : 0u; };
+      uint64_t v = (word(w) | (word(w + 1) << 32)) >> sh;
+      if (sh) v |= word(w + 2) << (64 - sh);
+      digits[d] = static_cast<double>(v & ((1ull << 52) - 1ull));
+    }
+  };
+  // 2^e mod n^2 by e doublings of 1, split into base-n digits (a, b) = (v mod n, v div n)
+  Words x(n2w.size(), 0);
+  x[0] = 1;
+  int e = 0;
+  const int targets[3] = {52 * K, 52 * K + h->w, 104 * K};      // R, 2^w R, R^2   (w < 52 K)
+  double* dstA[3] = {h->oneA, h->sA, h->r2A};
+  double* dstB[3] = {h->oneB, h->sB, h->r2B};
+  for (int tgt = 0; tgt < 3; tgt++) {
+    for (; e < targets[tgt]; e++) words_dbl_mod(x, n2w);
+    Words q, r;
+    words_divmod(x, rt.words, q, r);
+    to52(r, dstA[tgt]);
+    to52(q, dstB[tgt]);
+  }
+  if (!sq.pair52) {
+    cudaError_t ce = cudaMalloc(&sq.pair52, sizeof(PairConsts52Dev));
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaMalloc(pair constants)");
+  }
+  cudaError_t ce = cudaMemcpyAsync(sq.pair52, h, sizeof(PairConsts52Dev), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "upload pair constants");
+  sq.root_slot = root_slot;
+  return SCB_OK;
+}
+
+extern "C" int scb_modulus_link_square(scb_ctx* ctx, int square_slot, int root_slot) { return scb::link_square_modulus(ctx, square_slot, root_slot); }
 
 // -------------------------------------------------------------------------------------------------
 // launch helpers
@@ -461,6 +601,31 @@ int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, 
                                                                  static_cast<double*>(scratch), mul_in, out, kout, B, queue, prog, nprog, pw);
   char label[64];
   snprintf(label, sizeof(label), "k_modexp52<%d,%d>[e=%d]", L, TPI, ebits);
+  return ctx->launched(label);
+}
+
+// exponentiation modulo the square of `rt` (pair form, kernels_f64_pair.cuh)
+template <int L, int TPI>
+int launch_modexp52p(scb_ctx* ctx, const scb_ctx::Mod& sq, const scb_ctx::Mod& rt, const uint32_t* base, int kbase, const uint32_t* exp, int ewords,
+                     size_t estride, int ebits, uint32_t* out, int kout, size_t B) {
+  using GP = GeoPair<L, TPI>;
+  int wbits = window_bits_for(ebits);
+  int nprog = 0, pw = 0;
+  const uint16_t* prog = estride == 0 ? ctx->find_program(exp, &nprog, &pw, &wbits) : nullptr;
+  const size_t smem = sizeof(double) * GP::WARP_SMEM_WORDS64 * WARPS_PER_BLOCK;
+  const void* kfn = reinterpret_cast<const void*>(&k_modexp52p<L, TPI>);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const int gpb = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
+  int grid = ctx->grid_for(kfn, smem, B, gpb);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * modexp52p_scratch_doubles<L, TPI>(wbits) * sizeof(double), &scratch);
+  if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  k_modexp52p<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(rt.dev52, sq.pair52, base, kbase, exp, ewords, estride, ebits, wbits,
+                                                                  static_cast<double*>(scratch), out, kout, B, queue, prog, nprog, pw);
+  char label[64];
+  snprintf(label, sizeof(label), "k_modexp52p<%d,%d>[e=%d]", L, TPI, ebits);
   return ctx->launched(label);
 }
 
@@ -624,6 +789,18 @@ int scb::modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, con
                     const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   const scb_ctx::Mod& md = ctx->mod[slot];
   if (kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp: output narrower than the modulus");
+  // square modulus linked to its root: base-root pair form on the FP64 engine (half the digit products)
+  if (ctx->use_f64 && ctx->use_pair && md.root_slot >= 0 && md.pair52 && mul_in == nullptr && exp_bits >= 64) {
+    const scb_ctx::Mod& rt = ctx->mod[md.root_slot];
+    switch (rt.K52) {
+      case 20: return launch_modexp52p<10, 2>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      case 30: return launch_modexp52p<15, 2>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      case 40: return launch_modexp52p<10, 4>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      case 60: return launch_modexp52p<15, 4>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      case 80: return launch_modexp52p<10, 8>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      default: break;
+    }
+  }
   // FP64 engine for real exponentiations (it has no advantage for the few-bit exponents of the DGK blinding)
   if (ctx->use_f64 && md.K52 > 0 && exp_bits >= 64 && 32 * kbase <= 104 * md.K52) {
     switch (md.K52) {

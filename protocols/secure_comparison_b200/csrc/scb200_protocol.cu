@@ -242,6 +242,7 @@ extern "C" int scb_paillier_set_public(scb_ctx* ctx, const uint32_t* n, int kN) 
   if (rc) return rc;
   rc = scb_modulus_load(ctx, SCB_MOD_PAILLIER_N, n, kN);
   if (rc) return rc;
+  if ((rc = scb::link_square_modulus(ctx, SCB_MOD_PAILLIER_N2, SCB_MOD_PAILLIER_N))) return rc;
   KeysDev* hk = host_keys(ctx);
   hk->kN = kN;
   memset(hk->Nw, 0, sizeof(hk->Nw));
@@ -372,6 +373,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
     case SCB_OPT_PAILLIER_CRT: ctx->use_crt = value != 0; return SCB_OK;
     case SCB_OPT_MODEXP_FP64: ctx->use_f64 = value != 0; return SCB_OK;
     case SCB_OPT_SLIDING_WINDOWS: ctx->use_sliding = value != 0; return SCB_OK;
+    case SCB_OPT_SQUARE_MODULUS: ctx->use_pair = value != 0; return SCB_OK;
     case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }
@@ -458,6 +460,7 @@ extern "C" int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, con
   for (int h = 0; h < 2; h++) {
     if ((rc = scb_modulus_load(ctx, slotP[h], P[h].data(), kP))) return rc;
     if ((rc = scb_modulus_load(ctx, slotP2[h], P2[h].data(), kN))) return rc;
+    if ((rc = scb::link_square_modulus(ctx, slotP2[h], slotP[h]))) return rc;
     if (2 * W * ctx->mod[slotP[h]].K < 32 * kN || 2 * W * ctx->mod[slotP2[h]].K < 64 * kN)
       return fail(ctx, SCB_EINVAL, "scb_paillier_set_private_crt: primes too short for the double-width reductions");
   }

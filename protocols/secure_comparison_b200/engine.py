@@ -149,6 +149,15 @@ class Engine:
         self._moduli[slot] = (modulus, k)
         return k
 
+    def link_square(self, square_slot: int, root_slot: int) -> None:
+        """Declare ``square_slot`` (loaded with n^2) the square of ``root_slot`` (loaded with n): its exponentiations then
+        run in base-n pair form on the FP64 engine -- half the digit products, bit-identical results."""
+        self._check(self.lib.scb_modulus_link_square(self.ctx, square_slot, root_slot))
+
+    def set_square_modulus(self, enabled: bool) -> None:
+        """Pair-form exponentiation for linked square moduli (default) or n^2 as an ordinary modulus; bit-identical results."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_SQUARE_MODULUS, int(bool(enabled))))
+
     def modulus(self, slot: int) -> int:
         return self._moduli[slot][0]
 

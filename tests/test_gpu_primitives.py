@@ -60,6 +60,53 @@ def _modexp_matches_pow(eng, bits, ebits, B):
     assert limbs_to_ints(out) == [m * pow(b, e_shared, n) % n for b, m in zip(bases, muls)]
 
 
+# (root bits, exponent bits, batch): every pair-form geometry -- root K = 20 (10x2), 30 (15x2), 40 (10x4), 60 (15x4), 80 (10x8);
+# 1036 and 2076 bits are the sizes with the least Montgomery slack (R = 16 n)
+SQUARE_SIZES = [(512, 512, 40), (1024, 1024, 150), (1036, 200, 64), (1536, 160, 64), (2048, 2048, 100), (2076, 96, 40), (3072, 128, 40),
+                (4096, 300, 40), (100, 64, 33)]
+
+
+@pytest.mark.parametrize("bits,ebits,B", SQUARE_SIZES)
+def test_modexp_square_modulus_pair_form(eng, bits, ebits, B):
+    """Exponentiation modulo a linked square n^2 (base-n pair arithmetic, tests/pairmul_model.py) against Python's pow and
+    against the plain engine on the same slot; bases wider than n (reduced on load), per-element and shared exponents."""
+    rng = random.Random(bits * 13 + ebits)
+    n = rand_modulus(rng, bits)
+    root, sq = nat.MOD_USER0 + 1, nat.MOD_USER0 + 2
+    eng.load_modulus(root, n)
+    k2 = eng.load_modulus(sq, n * n, 2 * ((bits + 31) // 32))
+    eng.link_square(sq, root)
+    bases = [rng.randrange(n * n) for _ in range(B)]
+    bases[:6] = [0, 1, n * n - 1, n, n - 1, (1 << (32 * k2)) - 1 if (1 << (32 * k2)) - 1 < n * n else n + 1]
+    exps = [rng.getrandbits(ebits) for _ in range(B)]
+    exps[6:9] = [0, 1, (1 << ebits) - 1]
+    ew = (ebits + 31) // 32
+    want = [pow(b, e, n * n) for b, e in zip(bases, exps)]
+    out = eng.modexp(sq, ints_to_limbs(bases, k2), ints_to_limbs(exps, ew), ebits)
+    assert limbs_to_ints(out) == want
+    e_shared = rng.getrandbits(ebits) | (1 << (ebits - 1)) | 1
+    want_shared = [pow(b, e_shared, n * n) for b in bases]
+    out = eng.modexp(sq, ints_to_limbs(bases, k2), ints_to_limbs([e_shared], ew)[0], ebits)
+    assert limbs_to_ints(out) == want_shared
+    eng.set_sliding_windows(False)
+    try:
+        out = eng.modexp(sq, ints_to_limbs(bases, k2), ints_to_limbs([e_shared], ew)[0], ebits)
+        assert limbs_to_ints(out) == want_shared
+    finally:
+        eng.set_sliding_windows(True)
+    eng.set_square_modulus(False)                    # the same slot as an ordinary 2K-digit modulus
+    try:
+        out = eng.modexp(sq, ints_to_limbs(bases, k2), ints_to_limbs([e_shared], ew)[0], ebits)
+        assert limbs_to_ints(out) == want_shared
+    finally:
+        eng.set_square_modulus(True)
+    with pytest.raises(ValueError):
+        eng.link_square(root, sq)                    # not a square of that slot
+    eng.load_modulus(root, n)                        # reloading the root drops the link (results stay correct)
+    out = eng.modexp(sq, ints_to_limbs(bases[:8], k2), ints_to_limbs([e_shared], ew)[0], ebits)
+    assert limbs_to_ints(out) == want_shared[:8]
+
+
 @pytest.mark.parametrize("bits", [64, 1024, 2048, 3072, 4096, 8192])
 def test_modmul_and_edge_moduli(eng, bits):
     rng = random.Random(bits)

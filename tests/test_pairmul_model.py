@@ -1,0 +1,37 @@
+"""CPU pin of the square-modulus pair arithmetic (tests/pairmul_model.py = the data flow of csrc/kernels_f64_pair.cuh)
+against Python's pow, including the sizes with the least Montgomery slack and inputs wider than the modulus."""
+import random
+
+import pytest
+
+from pairmul_model import PairCtx
+from test_exponent_program import compile_program as compile_program_py
+
+
+def rand_odd(rng, bits):
+    return rng.getrandbits(bits) | (1 << (bits - 1)) | 1
+
+
+@pytest.mark.parametrize("bits", [100, 512, 1024, 1036, 1536, 2048, 2076, 4096])
+def test_pair_modexp_fixed_windows(bits):
+    rng = random.Random(bits)
+    n = rand_odd(rng, bits)
+    ctx = PairCtx(n)
+    assert ctx.R >= 16 * n
+    for trial in range(8):
+        in_bits = rng.choice([32 * ((bits + 31) // 32), 64 * ((bits + 31) // 32), 128 * ((bits + 31) // 32)])
+        x = [0, (n * n - 1) % (1 << in_bits), n, (1 << in_bits) - 1][trial] if trial < 4 else rng.getrandbits(in_bits)
+        ebits = rng.choice([1, 5, 17, 64, 160])
+        e = rng.getrandbits(ebits)
+        assert ctx.modexp_fixed(x, e, ebits, rng.choice([1, 2, 3, 4, 5]), in_bits) == pow(x, e, n * n)
+
+
+@pytest.mark.parametrize("bits,ebits", [(512, 512), (1024, 1024), (2048, 300)])
+def test_pair_modexp_sliding_program(bits, ebits):
+    rng = random.Random(bits + ebits)
+    n = rand_odd(rng, bits)
+    ctx = PairCtx(n)
+    e = rng.getrandbits(ebits) | (1 << (ebits - 1))
+    prog, w = compile_program_py(e)
+    for x in (0, 1, n - 1, n * n - 1, rng.randrange(n * n), rng.randrange(n)):
+        assert ctx.modexp_prog(x, prog, w, 64 * ((bits + 31) // 32)) == pow(x, e, n * n)
