@@ -14,16 +14,24 @@ scaling: B per GPU is fixed; NCCL only carries the barrier and the max-over-rank
 
 `value`   : comparisons/s with every input resident in HBM (device-pointer C-ABI entry points), CUDA
             events on the engine's stream, max over ranks.
-`e2e`     : the same through the host-buffer C-ABI calls (pinned host inputs; H2D of every input and D2H
-            of every message/result inside the timed region).
-`roofline`: integer-multiply pipe (IMAD.WIDE.U32 on the fmaheavy pipe), not HBM / tensor: DESIGN.md "Roofline".
+`e2e`     : the same metric through the reference-shaped public API -- `Initiator.perform_secure_comparison` and
+            `KeyHolder.perform_secure_comparison` as two coroutines over an in-memory communicator, packed wire
+            format: inputs from pinned HOST memory, every protocol message copied device -> host -> device, the
+            result read back, all inside the timed region (nonces from the device CSPRNG, the drivers' default).
+`roofline`: multiplier pipes (integer-multiply roofline of the north star), not HBM / tensor: DESIGN.md "Roofline".
+`parity`  : SURVEY 8d gates on the LAST TIMED step: (1) every boundary message (z_enc, z, [d],[beta_i], [c_i], delta_B,
+            enc3, result) of >= 4,096 seeded random indices bit-identical to the CPU oracle run on the same inputs and
+            nonces (all host cores; checker only), (2) decrypted bit == plaintext truth for 100 % of the batch.
+`config2` / `config3` (N > 1, or --extra-configs): BASELINE configs[2] (1,048,576 x l=32, sharded) and configs[3]
+            (262,144 x l=64, Paillier-4096 / DGK-3072, sharded): one warm-up + one timed step each, same two gates.
 
 The product path never touches ``oracle/``: keys come from a key file through the package's own loader.
-``oracle`` is imported only by the ``cpu_baseline`` leg and by ``--impl reference``.
+``oracle`` is imported only by the parity gate (after the timed region), the ``cpu_baseline`` leg and ``--impl reference``.
 """
 from __future__ import annotations
 
 import argparse
+import asyncio
 import json
 import os
 import subprocess
@@ -36,25 +44,53 @@ sys.path.insert(0, ROOT)
 
 METRIC = "secure comparisons/sec (Paillier-2048/DGK-2048, l=16)"   # the headline configuration; other --l / key sizes are labelled in `config`
 UNIT = "comparisons/s"
-KEY_FILE = os.path.join(ROOT, "tests", "golden", "keys_p2048_d2048_v160_l16.json")   # seeded synthetic key pair (data)
 
 
 def key_file(paillier_bits: int, dgk_bits: int, l: int) -> str:
-    """Seeded synthetic key pairs (data, committed under tests/golden): the headline configuration and the key sizes /
-    bit lengths of BASELINE configs[2] (l = 32) and configs[3] (Paillier-4096 / DGK-3072, l = 64)."""
-    return os.path.join(ROOT, "tests", "golden", f"keys_p{paillier_bits}_d{dgk_bits}_v160_l{l}.json")
-# Integer-multiply peak: IMAD.WIDE.U32 (32x32+64 -> 64) issues on the fmaheavy pipe only, 8 lanes/clk/SMSP =
-# 32 MAC/clk/SM (ncu: sm__pipe_fmaheavy_cycles_active; microbenchmark profiles/r01_imad_microbench2.jsonl measured
-# 8.6 TMAC/s sustained = 29.6/clk/SM at the nominal clock).  Peak used for `frac` = 148 SMs x 32 x 1.965 GHz.
+    """Seeded synthetic key pairs (committed under data/): the headline configuration and the key sizes / bit lengths of
+    BASELINE configs[2] (l = 32) and configs[3] (Paillier-4096 / DGK-3072, l = 64)."""
+    return os.path.join(ROOT, "data", f"keys_p{paillier_bits}_d{dgk_bits}_v160_l{l}.json")
+
+
+# Integer-multiply roofline of the north star: IMAD.WIDE.U32 (32x32+64 -> 64) issues on the fmaheavy pipe only, 8 lanes/clk/SMSP
+# = 32 MAC/clk/SM (what ncu's sm__pipe_fmaheavy pct_of_peak refers to): nominal = 148 SMs x 32 x 1.965 GHz.  The rate this GPU
+# actually sustains is measured at the start of every run through the library (scb_measure_peak) and reported beside it.
 INT_PEAK_MAC_PER_S = 148 * 32 * 1.965e9
-INT_PEAK_MEASURED_MAC_PER_S = 8.596e12
-# SURVEY.md section 8d algorithmic work, 32x32->64 MAC units (fixed-window modexp, k 32-bit limbs: (e + e/5 + 32)(2k^2 + k))
-MAC_PER_COMPARISON_L16 = 567e6      # reference-faithful operation list of one interactive comparison
-MAC_PER_MODEXP_4096_2048 = 81.91e6  # one rho^N mod N^2 (k = 128 limbs, 2048-bit exponent)
 # fixed (x, y) pairs of the reference's tests (test_secure_comparison.py:27-37), non-negative ones
 FIXED_PAIRS = [(0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7804), (8668, 9015), (23, 42), (42, 23), (7, 7), (0, 0)]
-# ncu --set full of k_modexp52<10,8> at B = 32768 (profiles/r01y_ncu_k_modexp52_10x8_final.txt): dram read + write bytes per launch
-NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 = (2.916283e9 + 1.426988e9) / 32768
+
+
+def mac_per_modexp(bits: int, ebits: int) -> float:
+    """SURVEY.md section 8d unit: fixed-window (w = 5) Montgomery modexp on k 32-bit limbs = (e + e/5 + 32)(2k^2 + k) MACs."""
+    k = bits // 32
+    return (ebits + -(-ebits // 5) + 32) * (2 * k * k + k)
+
+
+def mac_per_comparison(l: int, kN2: int, kn: int, kp: int, nbits: int, rand_bits: int, ubits: int, vbits: int = 160) -> float:
+    """SURVEY.md section 8d, reference-faithful operation list of one interactive comparison (inversions excluded)."""
+    mm = lambda k: 2 * k * k + k  # noqa: E731
+    fw = lambda e, k: (e + -(-e // 5) + 32) * mm(k)  # noqa: E731
+    return (5 * fw(nbits, kN2) + 2 * (l + 1) * fw(rand_bits, kn) + (l * (l - 1) // 2) * mm(kn) + 8 * l * mm(kn)
+            + (l + 1) * 1.5 * ubits * mm(kn) + (l + 1) * fw(vbits, kp))
+
+
+def executed_mac_per_comparison(l: int, kN: int, kn: int, kp: int, nbits: int, rand_bits: int, ubits: int, vbits: int = 160) -> float:
+    """Multiply-adds the engine actually EXECUTES per comparison, in the same 32x32 unit, counting its legitimate shortcuts
+    (CRT for the KeyHolder, fixed-base tables, pair form of the square moduli): k-limb Montgomery pass = 2k^2 + k.
+      rho^N mod N^2 in base-N pair form: 2 passes of kN limbs per squaring, 3 per window product (sliding window 7)
+      KeyHolder: 2 decrypt halves + 6 randomizer halves mod p^2 in pair form (kN/2 limbs, 1024-bit exponents, window 6),
+                 6 exponentiations mod p (kN/2 limbs)
+      DGK: 2(l+1) fixed-base randomizers of 25 products, fused vector kernel ~ (l(l-1)/2 + 10 l) products + blinding
+      is-zero: (l+1) exponentiations mod p_dgk (kp limbs, vbits exponent)."""
+    mm = lambda k: 2 * k * k + k  # noqa: E731
+    half = kN // 2
+    alice = (2 * nbits + 3 * (nbits / 8 + 64)) * mm(kN)
+    hb = nbits // 2
+    bob_pair = 8 * (2 * hb + 3 * (hb / 7 + 32)) * mm(half)
+    bob_plain = 6 * (hb + hb / 7 + 32) * mm(half)
+    dgk = 2 * (l + 1) * (-(-rand_bits // 16)) * mm(kn) + (l * (l - 1) // 2 + 10 * l) * mm(kn) + (l + 1) * 1.5 * ubits * mm(kn)
+    iszero = (l + 1) * (vbits + vbits / 5 + 16) * mm(kp)
+    return alice + bob_pair + bob_plain + dgk + iszero
 
 
 def _measured_hbm_gbs() -> float:
@@ -64,6 +100,19 @@ def _measured_hbm_gbs() -> float:
             return float(json.load(fh)["hbm_gbs"])
     except Exception:
         return 6650.0
+
+
+def ncu_traffic_bytes(kernel: str, B: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture of
+    THIS kernel (profiles/ncu_traffic.json, keyed by kernel name; bytes scale with the batch).  None when the kernel or
+    configuration has no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            table = json.load(fh)
+        ent = table.get(kernel)
+        return int(ent["dram_bytes"] * B / ent["batch"]) if ent else None
+    except Exception:
+        return None
 
 
 def parse_args():
@@ -77,8 +126,12 @@ def parse_args():
     ap.add_argument("--paillier-bits", type=int, default=2048)
     ap.add_argument("--dgk-bits", type=int, default=2048)
     ap.add_argument("--cpu-per-core", type=int, default=128, help="comparisons per host core in the CPU sample (~7 s per core at 2048 bits)")
+    ap.add_argument("--parity-sample", type=int, default=4096, help="indices of the timed batch checked message by message against the oracle (whole job)")
+    ap.add_argument("--extra-configs", action="store_true", help="run the configs[2] / configs[3] shard legs even at N = 1")
+    ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity-oracle", action="store_true", help="skip the oracle sample gate (the decrypted-bit gate always runs)")
     return ap.parse_args()
 
 
@@ -135,7 +188,7 @@ def make_workload(B: int, l: int, seed: int, eng):
     rng = np.random.default_rng(seed)
     x = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
     y = rng.integers(0, 1 << l, size=B, dtype=np.uint64)
-    fixed = FIXED_PAIRS + [((1 << l) - 1, (1 << l) - 1)]
+    fixed = [p for p in FIXED_PAIRS if max(p) < (1 << l)] + [((1 << l) - 1, (1 << l) - 1)]
     for i, (a, b) in enumerate(fixed[:B]):
         x[i], y[i] = a, b
     kN = eng.kN
@@ -155,9 +208,32 @@ def make_workload(B: int, l: int, seed: int, eng):
 
     rand_bits_n = eng._fixed_base[0][1]
     u = eng.u
-    # blinding exponents in [1, u-1]: odd values below 2^(bitlen(u)-1) (a subset of the range; the arithmetic is the same)
-    r_blind = rand_bits((B, l + 1, eng.rb_words), u.bit_length() - 1)
-    r_blind[..., 0] |= 1
+    # blinding exponents uniform in [1, u-1] (reference initiator.py:512): rejection sampling on bitlen(u) bits
+    ub = u.bit_length()
+    r_blind = rand_bits((B * (l + 1), eng.rb_words), ub)
+
+    def as_obj(a):
+        v = a[:, 0].astype(object)
+        for j in range(1, a.shape[1]):
+            v = v + (a[:, j].astype(object) << (32 * j))
+        return v
+
+    if eng.rb_words <= 2:
+        vals = r_blind[:, 0].astype(np.uint64) | ((r_blind[:, 1].astype(np.uint64) << np.uint64(32)) if eng.rb_words == 2 else np.uint64(0))
+        bad = (vals == 0) | (vals >= np.uint64(u))
+        while bad.any():
+            fresh = rand_bits((int(bad.sum()), eng.rb_words), ub)
+            r_blind[bad] = fresh
+            vals = r_blind[:, 0].astype(np.uint64) | ((r_blind[:, 1].astype(np.uint64) << np.uint64(32)) if eng.rb_words == 2 else np.uint64(0))
+            bad = (vals == 0) | (vals >= np.uint64(u))
+    else:                                               # l = 64: u ~ 2^66 needs three words
+        vals = as_obj(r_blind)
+        bad = np.array([(int(v) == 0) or (int(v) >= u) for v in vals], dtype=bool)
+        while bad.any():
+            r_blind[bad] = rand_bits((int(bad.sum()), eng.rb_words), ub)
+            vals = as_obj(r_blind)
+            bad = np.array([(int(v) == 0) or (int(v) >= u) for v in vals], dtype=bool)
+    r_blind = r_blind.reshape(B, l + 1, eng.rb_words)
     perm = np.argsort(rng.random((B, l + 1)), axis=1).astype(np.uint8)
     plain = np.zeros((2, B, kN), dtype=np.uint32)
     plain[0, :, 0] = (x & 0xFFFFFFFF).astype(np.uint32)
@@ -174,7 +250,129 @@ def make_workload(B: int, l: int, seed: int, eng):
         "rho_enc3": rand_limbs((B, 3, kN)),
     }
     truth = (x <= y).astype(np.uint8)
-    return w, truth
+    return w, truth, (x, y)
+
+
+class DevicePass:
+    """One batch resident in HBM and the six device-pointer C-ABI calls of a protocol pass over it."""
+
+    def __init__(self, eng, w, l):
+        import numpy as np
+        import torch
+
+        from protocols.secure_comparison_b200 import _native as nat
+        self.eng, self.l, self.np, self.torch, self.nat = eng, l, np, torch, nat
+        B = w["x"].shape[0]
+        self.B = B
+        kN, kc, kn = eng.kN, eng.kc, eng.kn
+
+        def dev(a):
+            return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+
+        self.d = {k: dev(v) for k, v in w.items()}
+        i32 = dict(dtype=torch.int32, device="cuda")
+        self.z_enc = torch.empty((B, kc), **i32)
+        self.z = torch.empty((B, kN), **i32)
+        self.db = torch.empty((B, l + 1, kn), **i32)
+        self.c = torch.empty((B, l + 1, kn), **i32)
+        self.delta_b = torch.empty((B,), dtype=torch.uint8, device="cuda")
+        self.enc3 = torch.empty((B, 3, kc), **i32)
+        self.res = torch.empty((B, kc), **i32)
+        self.bit = torch.empty((B, kN), **i32)
+        torch.cuda.synchronize()
+
+    def step(self):
+        eng, d, l, B, p = self.eng, self.d, self.l, self.B, self.nat._ptr
+        lib, ctx = eng.lib, eng.ctx
+        eng._check(lib.scb_initiator_step1_dev(ctx, p(d["x"]), p(d["y"]), p(d["r"]), p(d["rho_z"]), l, p(self.z_enc), B))
+        eng._check(lib.scb_paillier_decrypt_dev(ctx, p(self.z_enc), p(self.z), B))
+        eng._check(lib.scb_keyholder_step4ab_dev(ctx, p(self.z), l, p(d["rho_db"]), eng.rand_words, p(self.db), B))
+        eng._check(lib.scb_initiator_step4_dev(ctx, p(self.db), p(d["r"]), p(d["delta_a"]), p(d["r_blind"]), eng.rb_words, p(d["perm"]),
+                                               p(d["rho_c"]), eng.rand_words, l, p(self.c), B))
+        eng._check(lib.scb_keyholder_step4j_5_dev(ctx, p(self.c), p(self.z), p(d["rho_enc3"]), l, p(self.delta_b), p(self.enc3), B))
+        eng._check(lib.scb_initiator_step6_7_dev(ctx, p(self.enc3), p(d["r"]), p(d["delta_a"]), l, p(self.res), B))
+
+    def decrypted_bits_ok(self, truth) -> bool:
+        np, eng, p = self.np, self.eng, self.nat._ptr
+        eng._check(eng.lib.scb_paillier_decrypt_dev(eng.ctx, p(self.res), p(self.bit), self.B))
+        eng.sync()
+        bits = self.bit.cpu().numpy().view(np.uint32)
+        return bool(np.array_equal(bits[:, 0].astype(np.uint8), truth) and not bits[:, 1:].any())
+
+    def messages_at(self, indices):
+        """Rows of every boundary message of the last pass at the given indices (host limb arrays)."""
+        np, torch = self.np, self.torch
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64), device="cuda")
+
+        def rows(t):
+            a = t.index_select(0, idx).cpu().numpy()
+            return a.view(np.uint32) if a.dtype == np.int32 else a
+        return {"z_enc": rows(self.z_enc), "z": rows(self.z), "db": rows(self.db), "c": rows(self.c), "delta_b": rows(self.delta_b),
+                "enc3": rows(self.enc3), "result": rows(self.res)}
+
+
+def oracle_gate(key_spec, l, w, dp: DevicePass, n_indices: int, seed: int, processes=None) -> dict:
+    """SURVEY 8d gate (1): a seeded random sample of the batch the timed pass just processed, every boundary message against the
+    CPU oracle (checker only -- after the timed region)."""
+    import numpy as np
+
+    from oracle.parallel import check_messages_against_oracle
+    B = dp.B
+    n = min(n_indices, B)
+    indices = np.sort(np.random.default_rng(seed).choice(B, size=n, replace=False)) if n < B else np.arange(B)
+    t0 = time.perf_counter()
+    res = check_messages_against_oracle(key_spec, l, w, dp.messages_at(indices), [int(i) for i in indices], processes)
+    res["oracle_wall_s"] = round(time.perf_counter() - t0, 1)
+    res["sample_seed"] = seed
+    return res
+
+
+def timed_passes(eng, dp: DevicePass, steps: int, stream, barrier):
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            dp.step()
+        e1.record(stream)
+    eng.sync()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+# --------------------------------------------------------------------------------------------- extra configuration legs
+def run_config_leg(name, paillier_bits, dgk_bits, l, B, rank, world, local, parity_n, barrier, reduce_max, oracle_procs, do_oracle):
+    """One warm-up + one timed device-resident pass of another BASELINE configuration on this rank's shard, with both gates."""
+    import torch
+
+    from protocols.secure_comparison_b200 import SchemeEngine
+    from protocols.secure_comparison_b200.keyfile import schemes_from_json
+    paillier, dgk = schemes_from_json(key_file(paillier_bits, dgk_bits, l))
+    eng = SchemeEngine(local)
+    eng.load_paillier(paillier)
+    eng.load_dgk(dgk, l)
+    w, truth, _ = make_workload(B, l, seed=4321 + rank + 1000 * l, eng=eng)
+    dp = DevicePass(eng, w, l)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    dp.step()                                              # warm-up (grows every scratch buffer)
+    eng.sync()
+    before = eng.launch_count
+    ms = reduce_max(timed_passes(eng, dp, 1, stream, barrier))
+    launches = eng.launch_count - before
+    bits_ok = dp.decrypted_bits_ok(truth)
+    gate = None
+    if do_oracle and parity_n > 0:
+        gate = oracle_gate((paillier_bits, dgk_bits, 160, l), l, w, dp, parity_n, seed=97 + rank, processes=oracle_procs)
+    out = {"workload": f"{name}: {world * B} comparisons over {world} GPU(s) = {B} per GPU, l={l}, Paillier-{paillier_bits}/DGK-{dgk_bits}, interactive flow",
+           "value": round(world * B / (ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": 1, "warmup": 1, "batch_per_gpu": B,
+           "gpu_launches": int(launches),
+           "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B), "oracle_sample_rank0": gate}}
+    ok = bits_ok and (gate is None or gate["bit_identical"])
+    del dp
+    eng.close()
+    torch.cuda.empty_cache()
+    return out, ok
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -182,8 +380,8 @@ def run_ours(args):
     import numpy as np
     import torch
 
-    from protocols.secure_comparison_b200 import SchemeEngine
     from protocols.secure_comparison_b200 import _native as nat
+    from protocols.secure_comparison_b200 import get_engine, set_default_device
     from protocols.secure_comparison_b200.keyfile import schemes_from_json
     from protocols.secure_comparison_b200.sharding import shard_range
 
@@ -196,164 +394,177 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, l = args.batch, args.l
-    # weak scaling: the global batch is world * B comparisons; this rank owns the contiguous block [lo, hi)
-    lo, hi = shard_range(world * B, rank, world)
-    assert hi - lo == B
-    paillier, dgk = schemes_from_json(key_file(args.paillier_bits, args.dgk_bits, l))
-    eng = SchemeEngine(local)
-    eng.load_paillier(paillier)
-    eng.load_dgk(dgk, l)
-    w, truth = make_workload(B, l, seed=1234 + rank, eng=eng)
-    kN, kc, kn = eng.kN, eng.kc, eng.kn
-    stream = torch.cuda.ExternalStream(eng.stream_ptr)
-    lib, ctx = eng.lib, eng.ctx
-
-    def dev(a):
-        return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
-
-    d = {k: dev(v) for k, v in w.items()}
-    i32 = dict(dtype=torch.int32, device="cuda")
-    d_z_enc = torch.empty((B, kc), **i32)
-    d_z = torch.empty((B, kN), **i32)
-    d_db = torch.empty((B, l + 1, kn), **i32)
-    d_c = torch.empty((B, l + 1, kn), **i32)
-    d_delta_b = torch.empty((B,), dtype=torch.uint8, device="cuda")
-    d_enc3 = torch.empty((B, 3, kc), **i32)
-    d_res = torch.empty((B, kc), **i32)
-    d_bit = torch.empty((B, kN), **i32)
-    p = nat._ptr
-
-    def step_device():
-        eng._check(lib.scb_initiator_step1_dev(ctx, p(d["x"]), p(d["y"]), p(d["r"]), p(d["rho_z"]), l, p(d_z_enc), B))
-        eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_z_enc), p(d_z), B))
-        eng._check(lib.scb_keyholder_step4ab_dev(ctx, p(d_z), l, p(d["rho_db"]), eng.rand_words, p(d_db), B))
-        eng._check(lib.scb_initiator_step4_dev(ctx, p(d_db), p(d["r"]), p(d["delta_a"]), p(d["r_blind"]), eng.rb_words, p(d["perm"]),
-                                               p(d["rho_c"]), eng.rand_words, l, p(d_c), B))
-        eng._check(lib.scb_keyholder_step4j_5_dev(ctx, p(d_c), p(d_z), p(d["rho_enc3"]), l, p(d_delta_b), p(d_enc3), B))
-        eng._check(lib.scb_initiator_step6_7_dev(ctx, p(d_enc3), p(d["r"]), p(d["delta_a"]), l, p(d_res), B))
 
     def barrier():
         torch.cuda.synchronize()
-        eng.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(v: float) -> float:
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(flag: bool) -> bool:
+        if world == 1:
+            return flag
+        t = torch.tensor([1.0 if flag else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    B, l = args.batch, args.l
+    # weak scaling: the global batch is world * B comparisons; this rank owns the contiguous block [lo, hi)
+    lo, hi = shard_range(world * B, rank, world)
+    assert hi - lo == B
+    key_spec = (args.paillier_bits, args.dgk_bits, 160, l)
+    paillier, dgk = schemes_from_json(key_file(args.paillier_bits, args.dgk_bits, l))
+    set_default_device(local)                               # the drivers (e2e leg) find their engine through the schemes
+    eng = get_engine(paillier, dgk, l)
+    # ---- pipe ceilings measured on this GPU, this run (the integer roofline is not in MEASURED_PEAKS.json)
+    peaks = {"imad_wide_mac_per_s": eng.measure_peak("imad_wide"), "dfma_per_s": eng.measure_peak("dfma")}
+    w, truth, _ = make_workload(B, l, seed=1234 + rank, eng=eng)
+    kN, kc, kn = eng.kN, eng.kc, eng.kn
+    stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    dp = DevicePass(eng, w, l)
+    d = dp.d
+    p = nat._ptr
+    i32 = dict(dtype=torch.int32, device="cuda")
+
     # ---- warm-up (also grows every scratch buffer to its final size)
     for _ in range(max(args.warmup, 1)):
-        step_device()
+        dp.step()
     eng.sync()
     launches_before = eng.launch_count
 
     # ---- timed region, device resident
-    barrier()
     with ClockSampler(local) as clocks:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(args.steps):
-                step_device()
-            e1.record(stream)
-        eng.sync()
-        barrier()
-    ms_total = e0.elapsed_time(e1)
+        ms_total = timed_passes(eng, dp, args.steps, stream, barrier)
     launches = eng.launch_count - launches_before
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = reduce_max(ms_total)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- parity gate on the last step's output: decrypted bits == plaintext truth for 100 % of the batch
-    eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_res), p(d_bit), B))
-    eng.sync()
-    bits = d_bit.cpu().numpy().view(np.uint32)
-    bits_ok = bool(np.array_equal(bits[:, 0].astype(np.uint8), truth) and not bits[:, 1:].any())
+    # ---- parity gates on the last timed step's output
+    bits_ok = dp.decrypted_bits_ok(truth)                   # (2) decrypted bits == plaintext truth for 100 % of the batch
+    host_cores = os.cpu_count() or 1
+    oracle_procs = max(1, host_cores // world)
+    gate = None
+    if not args.no_parity_oracle:
+        per_rank = -(-args.parity_sample // world)
+        gate = oracle_gate(key_spec, l, w, dp, per_rank, seed=20261018 + rank, processes=oracle_procs)      # (1) ciphertext level
+    gate_ok = gate is None or gate["bit_identical"]
+    ref_res = dp.res.clone()
 
     # ---- per-kernel timing of one more step (one CUDA event after every launch, on the engine's stream) for the
-    #      roofline of the dominant kernel: k_step1 = B modexps rho^N mod N^2 (4096-bit modulus, 2048-bit exponent)
+    #      roofline of the dominant kernel: the B exponentiations rho^N mod N^2 of step_1 + randomize
     eng.profile_begin()
-    step_device()
+    dp.step()
     kernels = eng.profile_end()
     step_ms_prof = sum(k["ms"] for k in kernels.values())
     top_name = max(kernels, key=lambda k: kernels[k]["ms"])
-    # the B modexps rho^N mod N^2 of Initiator.step_1 + randomize: one launch of k_modexp52<10,8> (FP64 engine, default) or,
-    # with the IMAD engine, the modexp fused inside k_step1<18,8>
     ebits_N = eng.paillier_n.bit_length()
-    f64_names = [k for k in kernels if k.startswith("k_modexp52") and k.endswith(f"[e={ebits_N}]")]
-    fp64_engine = bool(f64_names)
-    k1_name = f64_names[0] if fp64_engine else "k_step1"
+    k1_names = [k for k in kernels if k.startswith(("k_modexp52p", "k_modexp52<", "k_modexp<")) and k.endswith(f"[e={ebits_N}]")]
+    k1_name = k1_names[0] if k1_names else "k_step1"
+    pair_form = k1_name.startswith("k_modexp52p")
+    fp64_engine = k1_name.startswith("k_modexp52")
     k1 = kernels.get(k1_name, {"ms": 0.0, "launches": 1})
     k1_ms = k1["ms"] / max(k1["launches"], 1)
     # algorithmic MACs of B randomizers rho^N mod N^2 (SURVEY 8d formula; 81.91 M each at Paillier-2048)
-    k1_mac = B * (ebits_N + -(-ebits_N // 5) + 32) * (2 * kc * kc + kc)
+    k1_mac = B * mac_per_modexp(32 * kc, ebits_N)
     achieved = k1_mac / (k1_ms * 1e-3) / 1e12 if k1_ms else 0.0
-    bytes_per_launch = B * (kN * 4 + kc * 4) if fp64_engine else B * (2 * kc * 4 + 2 * kN * 4 + kc * 4)
-    K52 = {4096: 80, 8192: 160}.get(64 * kN, (64 * kN + 4 + 51) // 52)
-    nprod = ebits_N + -(-ebits_N // 6) + 64                 # squarings + 6-bit-window products + table (2,455 at 2048 bits)
-    fp64_ops = B * nprod * (2 * K52 * K52 * 3 + K52 * 4)    # DFMA/DADD thread-instructions of one launch
+    bytes_per_launch = B * (kN * 4 + kc * 4)
+    # what the launch executes: pair form = 2 passes of K digits per squaring, 3 per window product (K = digits of N);
+    # plain form = one pass of 2K digits.  DFMA + DADD thread-instructions per K-digit pass: 3 per digit product, 2 K^2 products
+    K52 = {2048: 40, 4096: 80, 1024: 20, 3072: 60}.get(32 * kN, (32 * kN + 4 + 51) // 52)
+    nsq, nmul = ebits_N, ebits_N // 8 + 64
+    if pair_form:
+        passes = 2 * nsq + 3 * nmul
+        fp64_ops = B * passes * (2 * K52 * K52 * 3 + K52 * 4)
+        exec_mac = B * passes * (2 * kN * kN + kN)
+    else:
+        K2 = 2 * K52
+        fp64_ops = B * (nsq + nmul) * (2 * K2 * K2 * 3 + K2 * 4)
+        exec_mac = B * (nsq + nmul) * (2 * kc * kc + kc)
+    cmp_alg = mac_per_comparison(l, kc, kn, kn // 2, ebits_N, eng._fixed_base[0][1], eng.u.bit_length())
+    cmp_exec = executed_mac_per_comparison(l, kN, kn, kn // 2, ebits_N, eng._fixed_base[0][1], eng.u.bit_length())
+    traffic = ncu_traffic_bytes(k1_name.split("[")[0], B)
+    imad_meas, dfma_meas = peaks["imad_wide_mac_per_s"], peaks["dfma_per_s"]
     roofline = {
         "bound": "int-pipe",
         "bound_detail": "multiplier pipes, not hbm and not tensor (north star: integer-multiply roofline): " + (
-            "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick; throughput-limited on the DFMA + IADD3 instruction mix)"
+            "FP64 pipe used as an exact 52x52-bit integer multiplier (DFMA anchor trick)" + (", square modulus N^2 in base-N pair form" if pair_form else "")
             if fp64_engine else "int32-multiply pipe (IMAD.WIDE.U32 on fmaheavy)"),
         "kernel": k1_name, "kernel_share_of_step": round(k1["ms"] / step_ms_prof, 4) if step_ms_prof else None,
         "kernel_ms_per_launch": round(k1_ms, 3),
-        "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic)",
+        "achieved": round(achieved, 4), "peak": round(INT_PEAK_MAC_PER_S / 1e12, 3), "unit": "TMAC/s (32x32->64, algorithmic: SURVEY 8d, 81.91 M per 4096/2048-bit modexp)",
         "frac": round(achieved * 1e12 / INT_PEAK_MAC_PER_S, 4),
-        "peak_source": "integer-multiply roofline of the north star: IMAD.WIDE.U32 = 32 lanes/clk/SM x 148 SMs x 1.965 GHz (what ncu's fmaheavy "
-                       "pct_of_peak refers to; the IMAD microbenchmark on this pool sustains 8.6 TMAC/s, profiles/r01_imad_microbench2.jsonl)",
-        "frac_of_measured_microbench_peak": round(achieved * 1e12 / INT_PEAK_MEASURED_MAC_PER_S, 4),
+        "peak_source": "nominal integer-multiply roofline: IMAD.WIDE.U32 = 32 lanes/clk/SM x 148 SMs x 1.965 GHz (not in MEASURED_PEAKS.json); "
+                       "peak_measured_this_run = the same instruction stream timed on this GPU through the library (scb_measure_peak)",
+        "peak_measured_this_run": {"imad_wide_tmac_per_s": round(imad_meas / 1e12, 3), "dfma_tera_per_s": round(dfma_meas / 1e12, 3),
+                                   "imad_wide_per_clk_per_sm_at_1965MHz": round(imad_meas / 148 / 1.965e9, 2),
+                                   "dfma_per_clk_per_sm_at_1965MHz": round(dfma_meas / 148 / 1.965e9, 2)},
+        "frac_of_measured_imad_peak": round(achieved * 1e12 / imad_meas, 4) if imad_meas else None,
+        "executed": {"tmac_per_s": round(exec_mac / (k1_ms * 1e-3) / 1e12, 4) if k1_ms else None,
+                     "frac_of_int_peak": round(exec_mac / (k1_ms * 1e-3) / INT_PEAK_MAC_PER_S, 4) if k1_ms else None,
+                     "note": "multiply-adds this launch executes in the same 32x32 unit (pair form: 2 K-digit passes per squaring, 3 per window "
+                             "product, sliding window 7) -- the algorithmic figure above counts the reference-faithful 2K-limb fixed-window modexp"},
         "fp64_pipe_frac": round(fp64_ops / (k1_ms * 1e-3) / (148 * 64 * 1.965e9), 4) if (fp64_engine and k1_ms) else None,
-        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz); ncu: sm__pipe_fp64_cycles_active 62 %, "
-                          "ALU pipe 50 %, issue slots 60 % (profiles/r01y_ncu_k_modexp52_10x8_final.txt); a pure DFMA stream sustains 54.5/clk/SM, mixed 1:1 with "
-                          "integer adds 46.7 (profiles/r01_fp64_issue_microbench.jsonl)",
-        "imad_engine_reference": "same launch on the IMAD engine: 833 ms at B=65536 = 6.45 TMAC/s algorithmic, fmaheavy pipe 84-87 % busy "
-                                 "(profiles/r01e_ncu_k_step1.txt, profiles/r01s_ncu_k_modexp_imad_18x4.txt)",
-        "traffic": int(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B),
-        "traffic_note": "dram bytes per launch scaled from an ncu capture (window tables of the ~9,500 resident groups exceed L2): "
-                        "tens of GB/s, non-binding next to hbm_gbs = 6,550",
+        "fp64_pipe_frac_of_measured_dfma": round(fp64_ops / (k1_ms * 1e-3) / dfma_meas, 4) if (fp64_engine and k1_ms and dfma_meas) else None,
+        "fp64_pipe_note": "DFMA+DADD thread-instructions of the launch / (64 lanes/clk/SM x 148 x 1.965 GHz), and / the DFMA stream rate measured this run; "
+                          "ncu summaries of this kernel: profiles/ (README there)",
+        "traffic": traffic,
+        "traffic_note": "dram read+write bytes per launch from the committed ncu capture of this kernel (profiles/ncu_traffic.json), scaled by batch; "
+                        "null when this kernel/configuration has no capture",
         "hbm_peak_gbs_measured": _measured_hbm_gbs(),
-        "hbm_frac_of_measured": round(NCU_TRAFFIC_BYTES_PER_COMPARISON_STEP1 * B / (k1_ms * 1e-3) / 1e9 / _measured_hbm_gbs(), 5) if k1_ms else None,
+        "hbm_frac_of_measured": round(traffic / (k1_ms * 1e-3) / 1e9 / _measured_hbm_gbs(), 5) if (k1_ms and traffic) else None,
         "algorithmic_bytes": int(bytes_per_launch),
         "hbm_gbs_algorithmic": round(bytes_per_launch / (k1_ms * 1e-3) / 1e9, 2) if k1_ms else None,
-        "whole_step_frac": round(value / world * MAC_PER_COMPARISON_L16 / INT_PEAK_MAC_PER_S, 4),
-        "whole_step_note": "whole_step_frac counts the reference-faithful 567 M MAC per comparison against the INTEGER roofline; it exceeds 1 because the "
-                           "KeyHolder's CRT and the fixed-base tables do fewer multiply-adds for identical outputs and because the exponentiations run on the FP64 pipe",
+        "whole_step": {"algorithmic_mac_per_comparison": round(cmp_alg), "executed_mac_per_comparison": round(cmp_exec),
+                       "frac_algorithmic": round(value / world * cmp_alg / INT_PEAK_MAC_PER_S, 4),
+                       "frac_executed": round(value / world * cmp_exec / INT_PEAK_MAC_PER_S, 4),
+                       "note": "algorithmic = reference-faithful operation list (SURVEY 8d); executed = what the engine runs after CRT, fixed-base tables and the "
+                               "pair form of the square moduli (identical outputs); both against the nominal integer roofline"},
         "top_kernel_by_time": top_name,
         "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
     }
 
+    def one_timed_pass():
+        dp.step()
+        eng.sync()
+        with torch.cuda.stream(stream):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            dp.step()
+            a1.record(stream)
+        eng.sync()
+        return reduce_max(a0.elapsed_time(a1))
+
     # ---- the same pass with the exponentiations on the IMAD engine (the integer-pipe design of the north star; identical
     #      outputs): one warm-up pass, one timed pass, results compared bit for bit with the FP64-engine pass
-    ref_res = d_res.clone()
     eng.set_modexp_fp64(False)
-    step_device()
-    eng.sync()
-    with torch.cuda.stream(stream):
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record(stream)
-        step_device()
-        i1.record(stream)
-    eng.sync()
-    imad_ms = i0.elapsed_time(i1)
-    imad_same = bool(torch.equal(ref_res, d_res))
+    imad_ms = one_timed_pass()
+    imad_same = bool(torch.equal(ref_res, dp.res))
     eng.set_modexp_fp64(True)
-    if world > 1:
-        t = torch.tensor([imad_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        imad_ms = float(t.item())
     imad_engine = {"value": round(world * B / (imad_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(imad_ms, 3),
                    "bit_identical_to_fp64_engine": imad_same,
                    "note": "SCB_OPT_MODEXP_FP64 = 0: every exponentiation on the IMAD.WIDE engine (ncu: fmaheavy pipe 87 % busy, "
                            "profiles/r01s_ncu_k_modexp_imad_18x4.txt)"}
+    # ---- and with the square moduli treated as ordinary 2K-digit moduli on the FP64 engine (round 1's form; identical outputs)
+    eng.set_square_modulus(False)
+    plain_ms = one_timed_pass()
+    plain_same = bool(torch.equal(ref_res, dp.res))
+    eng.set_square_modulus(True)
+    plain_modulus = {"value": round(world * B / (plain_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(plain_ms, 3),
+                     "bit_identical_to_pair_form": plain_same, "note": "SCB_OPT_SQUARE_MODULUS = 0: N^2, p^2, q^2 as ordinary moduli"}
 
     # ---- production mode: every nonce drawn on the device (ChaCha20 CSPRNG keyed from `secrets`) INSIDE the timed pass,
     #      instead of the host-supplied nonce arrays the parity path uses; checked by decrypting all result bits
     eng.rng_seed()
     N_int, u_int = eng.paillier_n, eng.u
+    rand_bits_dgk = eng._fixed_base[0][1]
 
     def draw_nonces_device():
         eng.rng_below(N_int, B, kN, False, out=d["r"])
@@ -365,38 +576,30 @@ def run_ours(args):
         eng.rng_coins(B, out=d["delta_a"])
         eng.rng_permutations(l + 1, B, out=d["perm"])
 
-    rand_bits_dgk = eng._fixed_base[0][1]
     saved = {k: d[k].clone() for k in ("r", "rho_z", "rho_enc3", "r_blind", "rho_c", "rho_db", "delta_a", "perm")}
     draw_nonces_device()
-    step_device()
+    dp.step()
     eng.sync()
     with torch.cuda.stream(stream):
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record(stream)
         draw_nonces_device()
-        step_device()
+        dp.step()
         r1.record(stream)
     eng.sync()
-    rng_ms = r0.elapsed_time(r1)
-    eng._check(lib.scb_paillier_decrypt_dev(ctx, p(d_res), p(d_bit), B))
-    eng.sync()
-    rbits = d_bit.cpu().numpy().view(np.uint32)
-    rng_ok = bool(np.array_equal(rbits[:, 0].astype(np.uint8), truth) and not rbits[:, 1:].any())
+    rng_ms = reduce_max(r0.elapsed_time(r1))
+    rng_ok = dp.decrypted_bits_ok(truth)
     for k, v in saved.items():
-        d[k].copy_(v)                                   # back to the host-supplied nonces for the parity / e2e comparisons below
+        d[k].copy_(v)                                   # back to the host-supplied nonces for the comparisons below
     torch.cuda.synchronize()
-    step_device()
+    dp.step()
     eng.sync()
-    if world > 1:
-        t = torch.tensor([rng_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rng_ms = float(t.item())
     device_nonces = {"value": round(world * B / (rng_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(rng_ms, 3),
                      "decrypted_bits_match_truth": rng_ok,
                      "note": "nonces (r, rho's, r_i, delta_A, permutations) generated on the GPU inside the timed pass: scb_rng_* (ChaCha20)"}
 
     # ---- second half of the BASELINE metric: 2048-bit modexp/s (full-length per-element exponents, modulus = DGK n),
-    #      device resident, k_modexp<18,4>, SURVEY 8d unit = 20.56 M MAC per modexp
+    #      device resident, SURVEY 8d unit = 20.56 M MAC per modexp
     MB = B
     g = torch.Generator(device="cuda").manual_seed(99 + rank)
     d_mb = torch.randint(-2 ** 31, 2 ** 31 - 1, (MB, kn), dtype=torch.int32, device="cuda", generator=g)
@@ -417,46 +620,79 @@ def run_ours(args):
         modexp_pass()
         m1.record(stream)
     eng.sync()
-    mx_ms = m0.elapsed_time(m1) / 2
-    if world > 1:
-        t = torch.tensor([mx_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mx_ms = float(t.item())
+    mx_ms = reduce_max(m0.elapsed_time(m1) / 2)
     modexp_rate = world * MB / (mx_ms * 1e-3)
     modexp_2048 = {"value": round(modexp_rate, 1), "unit": "modexp/s", "bits": 32 * kn, "exponent_bits": 32 * kn, "batch_per_gpu": MB,
-                   "ms": round(mx_ms, 3), "frac_of_int_peak": round(modexp_rate / world * 20.56e6 / INT_PEAK_MAC_PER_S, 4)}
+                   "ms": round(mx_ms, 3), "frac_of_int_peak": round(modexp_rate / world * mac_per_modexp(32 * kn, 32 * kn) / INT_PEAK_MAC_PER_S, 4)}
+    del d_mb, d_me, d_mo
 
-    # ---- e2e: host buffers through the synchronous C-ABI calls (H2D + D2H inside the timed region)
+    # ---- e2e: the reference-shaped drivers over an in-memory communicator (packed wire format), pinned host inputs
     e2e = None
     if not args.no_e2e:
-        h = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory().numpy() for k, v in w.items()}
-        h = {k: (v.view(np.uint32) if v.dtype == np.int32 else v) for k, v in h.items()}
+        from protocols.secure_comparison_b200 import InMemoryCommunicator, Initiator, KeyHolder
+        hx = torch.from_numpy(w["x"].view(np.int32)).pin_memory().numpy().view(np.uint32)
+        hy = torch.from_numpy(w["y"].view(np.int32)).pin_memory().numpy().view(np.uint32)
+        store = {}
+        alice = Initiator(l, InMemoryCommunicator(store), "bob", wire_format=True)
+        bob = KeyHolder(l, InMemoryCommunicator(store), "alice", scheme_paillier=paillier, scheme_dgk=dgk, wire_format=True)
 
-        # the public host-buffer API: LocalPipeline = the five party-phases through the synchronous host-pointer C-ABI calls,
-        # batch split in two halves over two contexts (streams) so that one half's PCIe copies overlap the other's kernels
-        from protocols.secure_comparison_b200.pipeline import LocalPipeline
-        pipe = LocalPipeline(paillier, dgk, l, device=local, n_contexts=2, chunks=2)    # best of tools/time_pipeline.py
-        res = pipe.arena.empty((B, kc))
+        async def session(a_nonces=None, b_nonces=None):
+            return (await asyncio.gather(alice.perform_secure_comparison(hx, hy, a_nonces), bob.perform_secure_comparison(b_nonces)))[0]
 
-        pipe.compare(h, res)                      # warm-up: scratch growth, pinned result buffers
+        loop = asyncio.new_event_loop()
+        # parity run (untimed): injected host nonces -> bit-identical to the device-resident pass
+        a_n = {k: w[k] for k in ("r", "rho_z", "delta_a", "r_blind", "perm", "rho_c")}
+        b_n = {"rho_db": w["rho_db"], "rho_enc3": w["rho_enc3"]}
+        res = loop.run_until_complete(session(a_n, b_n))
+        same = bool(np.array_equal(np.asarray(res), dp.res.cpu().numpy().view(np.uint32)))
+        loop.run_until_complete(session())               # warm-up with device nonces (pinned message buffers now cached)
+        h2d0, d2h0 = eng.pool.h2d_bytes, eng.pool.d2h_bytes
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pipe.compare(h, res)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        E = (l + 1) * kn * 4
-        h2d = B * (2 * kc * 4 + 2 * kN * 4) + B * kc * 4 + B * (kN * 4 + (l + 1) * eng.rand_words * 4) + \
-            B * (E + kN * 4 + 1 + (l + 1) * (eng.rb_words * 4 + 1 + eng.rand_words * 4)) + B * (E + kN * 4 + 3 * kN * 4) + B * (3 * kc * 4 + kN * 4 + 1)
-        d2h = B * kc * 4 + B * kN * 4 + B * E + B * E + B * (1 + 3 * kc * 4) + B * kc * 4
-        same = bool(np.array_equal(res, d_res.cpu().numpy().view(np.uint32)))
+            res = loop.run_until_complete(session())
+        dt = reduce_max(time.perf_counter() - t0)
+        loop.close()
+        h2d = (eng.pool.h2d_bytes - h2d0) // args.steps
+        d2h = (eng.pool.d2h_bytes - d2h0) // args.steps
+        bits = eng.paillier_decrypt(np.asarray(res))
+        e2e_ok = bool(np.array_equal(bits[:, 0].astype(np.uint8), truth) and not bits[:, 1:].any())
         e2e = {"value": round(world * B * args.steps / dt, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": round(dt / args.steps * 1e3, 2), "matches_device_path": same,
-               "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 2 chunks, pinned buffers)"}
+               "ms_per_step": round(dt / args.steps * 1e3, 2), "decrypted_bits_match_truth": e2e_ok,
+               "matches_device_path_with_injected_nonces": same, "fraction_of_device_resident_value": round(world * B * args.steps / dt / value, 4),
+               "api": "Initiator.perform_secure_comparison + KeyHolder.perform_secure_comparison (two coroutines, InMemoryCommunicator, wire_format=True): "
+                      "x, y from pinned host memory, 4 protocol messages device->host->device, result device->host; nonces from the device CSPRNG"}
+        # secondary: the chunked host-buffer pipeline (round 1's e2e path), host-supplied nonces
+        from protocols.secure_comparison_b200.pipeline import LocalPipeline
+        h = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory().numpy() for k, v in w.items()}
+        h = {k: (v.view(np.uint32) if v.dtype == np.int32 else v) for k, v in h.items()}
+        pipe = LocalPipeline(paillier, dgk, l, device=local, n_contexts=2, chunks=2)
+        res2 = pipe.arena.empty((B, kc))
+        pipe.compare(h, res2)
+        barrier()
+        t0 = time.perf_counter()
+        pipe.compare(h, res2)
+        dt2 = reduce_max(time.perf_counter() - t0)
+        e2e["local_pipeline"] = {"value": round(world * B / dt2, 2), "unit": UNIT, "ms_per_step": round(dt2 * 1e3, 2),
+                                 "matches_device_path": bool(np.array_equal(res2, dp.res.cpu().numpy().view(np.uint32))),
+                                 "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 2 chunks, host-supplied nonces)"}
         pipe.close()
+        del h
+
+    # ---- BASELINE configs[2] and configs[3]: shard legs (N > 1, or on request)
+    extra = {}
+    extra_ok = True
+    if (world > 1 or args.extra_configs) and not args.no_extra_configs:
+        del dp, d, saved
+        from protocols.secure_comparison_b200 import reset_engines
+        reset_engines()
+        torch.cuda.empty_cache()
+        do_oracle = not args.no_parity_oracle
+        for name, pb, db_, ll, total, sample in (("config2", 2048, 2048, 32, 1048576, 4096), ("config3", 4096, 3072, 64, 262144, 1024)):
+            shard = max(1, total // max(world, 2 if args.extra_configs and world == 1 else 1) // (4 if world == 1 else 1))
+            leg, ok = run_config_leg(name, pb, db_, ll, shard, rank, world, local, -(-sample // world), barrier, reduce_max, oracle_procs, do_oracle)
+            extra[name] = leg
+            extra_ok = extra_ok and ok
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle as the timed CPU port, never on the product path
     cpu = None
@@ -466,26 +702,34 @@ def run_ours(args):
         cpu["modexp_2048_per_s_per_core"] = time_modexp(2048, 96)["modexp_per_s_per_core"]     # full-length exponent, mpz_powm, one core
         cpu["speedup_e2e_vs_all_cores"] = (e2e["value"] / cpu["value"]) if e2e else None
         cpu["speedup_e2e_vs_one_core"] = (e2e["value"] / cpu["per_core_comparisons_per_s"]) if e2e else None
+        cpu["target_reading"] = ("north star target '>= 1000x the reference's CPU on 8 x B200': claimed against ALL host cores of the box running the port "
+                                 "(speedup_e2e_vs_all_cores x 8 GPUs / cores ratio is what SCALE shows); the single-process reference runs on ONE core "
+                                 "(speedup_e2e_vs_one_core)")
         cpu = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in cpu.items()}
 
+    ok_all = all_ok(bits_ok and gate_ok and extra_ok)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "exact integers: 52-bit digits in f64 (exponentiations) + 29-bit digits in u32/u64 (everything else)",
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "exact integers: 52-bit digits in f64 (exponentiations) + 29-bit digits in u32/u64 (everything else)",
             "data": "synthetic (seeded keys, inputs and host-supplied nonces)",
             "config": {"workload": f"batch of {B} comparisons per GPU, l={l}, Paillier-{args.paillier_bits}/DGK-{args.dgk_bits} (v=160), interactive flow (all randomize() calls)",
                        "inputs_vs_l2": "per-step working set ~1.4 GB >> 126 MB L2", "batch_per_gpu": B, "l": l,
                        "sharding": "contiguous block of the global batch per rank, no data-path collective"},
-            "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B)},
+            "parity": {"decrypted_bits_match_truth": bits_ok, "checked": int(B),
+                       "oracle_sample": gate, "all_ranks_green": ok_all,
+                       "note": "oracle_sample = rank 0's share of the >= --parity-sample indices of the LAST TIMED step, every boundary message vs the CPU oracle"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "modexp_2048": modexp_2048, "imad_engine": imad_engine, "device_nonces": device_nonces,
-            "modexp_4096_per_s": round(B / (k1_ms * 1e-3), 1) if k1_ms else None,
+            "modexp_2048": modexp_2048, "imad_engine": imad_engine, "plain_modulus_form": plain_modulus, "device_nonces": device_nonces,
+            "modexp_4096_per_s": round(world * B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    if not bits_ok:
-        raise SystemExit("bench.py: parity gate failed (decrypted bits differ from the plaintext truth)")
+    if not ok_all:
+        raise SystemExit("bench.py: parity gate failed (see `parity` / `config2` / `config3` in the JSON line)")
 
 
 # --------------------------------------------------------------------------------------------- reference arm

@@ -60,6 +60,9 @@ const char* scb_last_error(const scb_ctx* ctx);
 int scb_sync(scb_ctx* ctx);                       /* wait for everything enqueued by *_dev calls */
 void* scb_stream(scb_ctx* ctx);                   /* the context's cudaStream_t (for event timing) */
 int scb_version(void);
+/* SHA-256 prefix over the library's sources, the header and the compiler flags it was built from (build.py rebuilds when it
+ * differs from the tree's). */
+const char* scb_build_id(void);
 /* number of kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 unsigned long long scb_launch_count(const scb_ctx* ctx);
 /* Per-kernel device timing.  Between scb_profile_begin and scb_profile_end one CUDA event is recorded on the
@@ -67,6 +70,11 @@ unsigned long long scb_launch_count(const scb_ctx* ctx);
  * {"kernel": {"ms": total, "launches": n}, ...} (time of a kernel = gap to the previous event). */
 int scb_profile_begin(scb_ctx* ctx);
 int scb_profile_end(scb_ctx* ctx, char* json_out, size_t json_bytes);
+/* Measured issue-rate ceiling of one multiplier pipe on THIS GPU, in thread-level operations per second: a register-resident
+ * stream of accumulating IMAD.WIDE.U32 (one 32x32+64 multiply-add each: the integer-multiply roofline of bench.py) or of DFMA
+ * (the FP64 engine's multiplier).  Takes a few milliseconds. */
+enum { SCB_PEAK_IMAD_WIDE = 0, SCB_PEAK_DFMA = 1 };
+int scb_measure_peak(scb_ctx* ctx, int which, double* ops_per_second);
 /* pinned host memory for callers that want DMA-able staging buffers */
 int scb_host_alloc(size_t bytes, void** out);
 int scb_host_free(void* ptr);

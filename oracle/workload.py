@@ -20,8 +20,15 @@ REFERENCE_PAIRS = [(-400, -383), (-1, 0), (0, 2), (1, 10), (230, 269), (1508, 24
                    (8668, 9015)]
 
 
+DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(GOLDEN_DIR)), "data")
+
+
 def key_file(paillier_bits: int, dgk_bits: int, v_bits: int, l: int) -> str:
-    return os.path.join(GOLDEN_DIR, f"keys_p{paillier_bits}_d{dgk_bits}_v{v_bits}_l{l}.json")
+    """Seeded key pairs: the three BASELINE key sizes live under ``data/`` (bench.py's product path loads them through the
+    package's own key-file reader); the small test-size pairs under ``tests/golden/``."""
+    name = f"keys_p{paillier_bits}_d{dgk_bits}_v{v_bits}_l{l}.json"
+    in_data = os.path.join(DATA_DIR, name)
+    return in_data if os.path.exists(in_data) else os.path.join(GOLDEN_DIR, name)
 
 
 def schemes_to_dict(paillier: Paillier, dgk: DGK) -> Dict[str, str]:

@@ -36,9 +36,11 @@ _SIGNATURES = {
     "scb_sync": ([_vp], ctypes.c_int),
     "scb_stream": ([_vp], _vp),
     "scb_version": ([], ctypes.c_int),
+    "scb_build_id": ([], ctypes.c_char_p),
     "scb_launch_count": ([_vp], ctypes.c_ulonglong),
     "scb_profile_begin": ([_vp], ctypes.c_int),
     "scb_profile_end": ([_vp, ctypes.c_char_p, ctypes.c_size_t], ctypes.c_int),
+    "scb_measure_peak": ([_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)], ctypes.c_int),
     "scb_host_alloc": ([ctypes.c_size_t, ctypes.POINTER(_vp)], ctypes.c_int),
     "scb_host_free": ([_vp], ctypes.c_int),
     "scb_dev_alloc": ([_vp, ctypes.c_size_t, ctypes.POINTER(_vp)], ctypes.c_int),

@@ -44,7 +44,7 @@ class InMemoryCommunicator:
 
     async def send(self, party_id: str, message: Any, msg_id: Optional[str] = None) -> None:
         if self.log is not None:
-            size = len(message) if isinstance(message, (bytes, bytearray)) else int(getattr(message, "nbytes", 0))
+            size = int(getattr(message, "nbytes", 0)) or (len(message) if isinstance(message, (bytes, bytearray)) else 0)
             self.log.append((str(msg_id), type(message).__name__, size))
         self.mailbox[str(msg_id)] = message
 

@@ -35,95 +35,20 @@ struct PairConsts52Dev {
   double sA[MAXK52], sB[MAXK52];       // 2^w R mod n^2        (Montgomery form of the Horner radix)
 };
 
-constexpr int PASS_SAVE = 1;     // store the complemented quotient digits of this pass (pass 1)
-constexpr int PASS_INJECT = 2;   // add the stored complement (+1) into the low column of every row (pass 2)
-
 template <int L, int TPI>
 struct GeoPair {
   static constexpr int K = L * TPI;
   static constexpr int GPW = 32 / TPI;
-  static constexpr int S2_OFF = (K + 1) * GPW;           // second streamed-operand area
-  static constexpr int Q_OFF = 2 * (K + 1) * GPW;        // complemented quotient digits of pass 1 (uint64)
-  static constexpr int WARP_SMEM_WORDS64 = (3 * K + 2) * GPW;
+  static constexpr int S2_OFF = (K + 2) * GPW;           // second streamed-operand area (each: K digits + 2 zero rows)
+  static constexpr int Q_OFF = 2 * (K + 2) * GPW;        // complemented quotient digits of pass 1 (uint64; K + 1 zero row)
+  static constexpr int WARP_SMEM_WORDS64 = (3 * K + 5) * GPW;
 };
 
-// The row loop of mmd_rows() (bn52.cuh) with the two hooks of the pair arithmetic, returning the UNRESOLVED columns so
-// that the caller can add further K-digit terms before the one carry resolution.  flags is warp-uniform.
+// The row loop with the two hooks of the pair arithmetic: bn52.cuh, mmd_rows_core<L, TPI, true>.
 template <int L, int TPI>
 __device__ __forceinline__ void mmd_rows_pair(const double (&av)[L], const double (&nv)[L], const double np, const double* __restrict__ sm_stream,
                                               uint64_t* __restrict__ sm_q, const int flags, uint64_t (&col)[L], uint64_t& hi_last) {
-  constexpr int GPW = Geo52<L, TPI>::GPW;
-  const int t = (threadIdx.x & 31) % TPI;
-  const bool top = t == TPI - 1;
-  const bool low_lane = t == 0;
-  const bool save = (flags & PASS_SAVE) != 0, inject = (flags & PASS_INJECT) != 0;
-  const double C1 = SCB_2P104, C12 = SCB_2P104 + SCB_2P52;
-  uint64_t AL[L], AH[L];
-#pragma unroll
-  for (int i = 0; i < L; i++) {
-    AL[i] = 0ull - 2ull * (i + 1) * BITS_2P52;
-    AH[i] = 0ull - 2ull * (i + 1) * BITS_2P104;
-  }
-  if (inject && low_lane) AL[0] += 1ull;                 // the "+ 1" of R - m = complement(m) + 1
-  const double* bp = sm_stream;
-  uint64_t* qp = sm_q;
-  double bj = bp[0];
-#pragma unroll 1
-  for (int blk = 0; blk < TPI; blk++) {
-#pragma unroll
-    for (int rr = 0; rr < L; rr++) {
-      bp += GPW;
-      const double bnext = bp[0];
-      {
-        const double hi = __fma_rz(av[0], bj, C1);
-        const double lo = __fma_rz(av[0], bj, __dsub_rn(C12, hi));
-        AH[rr % L] += raw(hi);
-        AL[rr % L] += raw(lo);
-      }
-      if (inject) {
-        const uint64_t c = qp[0];
-        if (low_lane) AL[rr % L] += c;
-      }
-      const double v0 = u52_to_double(AL[rr % L] & MASK52);
-      const double qh = __fma_rz(v0, np, C1);
-      double q = __fma_rz(v0, np, __dsub_rn(C1, qh));
-      q = __shfl_sync(FULL, q, 0, TPI);
-      if (save) {
-        if (low_lane) qp[0] = double_to_u52(q) ^ MASK52;
-      }
-      qp += GPW;
-#pragma unroll
-      for (int i = 1; i < L; i++) {
-        const double hi = __fma_rz(av[i], bj, C1);
-        const double lo = __fma_rz(av[i], bj, __dsub_rn(C12, hi));
-        AH[(i + rr) % L] += raw(hi);
-        AL[(i + rr) % L] += raw(lo);
-      }
-#pragma unroll
-      for (int i = 0; i < L; i++) {
-        const double hi = __fma_rz(nv[i], q, C1);
-        const double lo = __fma_rz(nv[i], q, __dsub_rn(C12, hi));
-        AH[(i + rr) % L] += raw(hi);
-        AL[(i + rr) % L] += raw(lo);
-      }
-      const uint64_t t0 = AL[rr % L];
-      AL[(1 + rr) % L] += AH[rr % L] + (t0 >> 52);
-      const uint64_t low = t0 & MASK52;
-      const uint64_t in = __shfl_down_sync(FULL, low, 1, TPI);
-      AL[rr % L] = (top ? 0ull : in) - 2ull * L * BITS_2P52;
-      AH[rr % L] = 0ull - 2ull * L * BITS_2P104;
-      bj = bnext;
-    }
-  }
-#pragma unroll
-  for (int p = 0; p < L; p++) {
-    AL[p] += 2ull * (p + 1) * BITS_2P52;
-    AH[p] += 2ull * (p + 1) * BITS_2P104;
-  }
-  col[0] = AL[0];
-#pragma unroll
-  for (int p = 1; p < L; p++) col[p] = AL[p] + AH[p - 1];
-  hi_last = AH[L - 1];
+  mmd_rows_core<L, TPI, true>(av, nv, np, sm_stream, sm_q, flags, col, hi_last);
 }
 
 // col += the lane's digits of (n - 1)   (n is odd: only digit 0 of the whole number changes)
@@ -530,6 +455,10 @@ k_modexp52p(const Modulus52Dev* __restrict__ m, const PairConsts52Dev* __restric
   using GP = GeoPair<L, TPI>;
   constexpr int K = Geo52<L, TPI>::K;
   double* sm_group = smem52 + (threadIdx.x >> 5) * GP::WARP_SMEM_WORDS64 + (threadIdx.x & 31) / TPI;
+  zero_pad_rows52<L, TPI>(sm_group);
+  zero_pad_rows52<L, TPI>(sm_group + GP::S2_OFF);
+  if ((threadIdx.x & 31) % TPI == 0) reinterpret_cast<uint64_t*>(sm_group + GP::Q_OFF)[K * GP::GPW] = 0ull;
+  __syncwarp();
   const size_t slot = GI::slot();
   double* XA = scratch + slot * modexp52p_scratch_doubles<L, TPI>(wbits);
   double* XB = XA + K;

@@ -238,7 +238,11 @@ unsigned long long* scb_ctx::fresh_queue() {
 // -------------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------------
-extern "C" int scb_version(void) { return 100; }
+extern "C" int scb_version(void) { return 200; }
+#ifndef SCB_BUILD_ID
+#define SCB_BUILD_ID "unversioned"
+#endif
+extern "C" const char* scb_build_id(void) { return SCB_BUILD_ID; }
 
 extern "C" int scb_ctx_create(int device, scb_ctx** out) {
   if (!out) return SCB_EINVAL;

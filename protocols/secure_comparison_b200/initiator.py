@@ -2,10 +2,12 @@
 (``tno/mpc/protocols/secure_comparison/initiator.py:15-564``), every argument being a batch.
 
 Batch containers: ``[B][k]`` uint32 limb arrays (preferred), or sequences of scheme ciphertext objects /
-ints (converted once at the surface).  Bit vectors are ``[B][l]`` uint8 arrays, LSB first.  Every random
+ints (converted once at the surface); every ciphertext result is a ``BatchedPaillierCiphertext`` /
+``BatchedDGKCiphertext`` (``ciphertexts.py``: a limb array that also carries the scheme, the ``fresh`` flag and the
+reference's ``+ - *`` operator algebra).  Bit vectors are ``[B][l]`` uint8 arrays, LSB first.  Every random
 choice of the reference (``secrets.randbelow`` / ``choice`` at initiator.py:223,250,420,512) can be injected
 through keyword arguments so that the CUDA path can be compared bit for bit with the CPU oracle; when
-left out it is drawn from ``secrets`` exactly like the reference.
+left out it is drawn by the device CSPRNG (ChaCha20 keyed from ``secrets``, ``csrc/scb200_rng.cu``).
 
 The individual ``step_*`` methods mirror the reference one to one and are built from the engine's
 batched primitives; ``steps_4c_to_4i`` and ``steps_6_7`` are the fused single-launch-sequence phases
@@ -19,10 +21,12 @@ from typing import Any, Optional, Tuple
 import numpy as np
 
 from . import _native as nat
+from .ciphertexts import BatchedDGKCiphertext, BatchedPaillierCiphertext, dgk_batch, paillier_batch
 from .communicator import Communicator
 from .limbs import int_to_limbs, ints_to_limbs
 from .schemes import SchemeEngine, as_limbs, get_engine
-from .utils import less_than_const, low_bits, random_below, random_bits, random_permutations, shift_right, to_bits_batch
+from .sessions import InitiatorSession
+from .utils import less_than_const, low_bits, random_permutations, shift_right, to_bits_batch
 
 
 def _bits(a) -> np.ndarray:
@@ -35,6 +39,8 @@ def _scheme_of(container, fallback=None):
     explicitly, or the one already loaded in the engine, is used)."""
     if fallback is not None:
         return fallback
+    if getattr(container, "scheme", None) is not None:
+        return container.scheme
     item = container
     while isinstance(item, (list, tuple)) and item:
         item = item[0]
@@ -68,9 +74,17 @@ class Initiator:
         return self._scheme_dgk
 
     # ------------------------------------------------------------------ driver (initiator.py:69-203)
-    async def perform_secure_comparison(self, x, y, nonces: Optional[dict] = None) -> np.ndarray:
-        """All of Alice's steps for a BATCH of comparisons, with the reference's message ids.
-        ``x`` / ``y``: batches of Paillier ciphertexts (limb arrays or sequences).  Returns ``[B][2kN]``."""
+    async def perform_secure_comparison(self, x, y, nonces: Optional[dict] = None) -> BatchedPaillierCiphertext:
+        """All of Alice's steps for a BATCH of comparisons, with the reference's message ids (``initiator.py:69-175``).
+
+        ``x`` / ``y``: batches of Paillier ciphertexts (containers, ``[B][2kN]`` limb arrays, sequences of scheme ciphertext
+        objects) or -- like the reference, ``initiator.py:93-102`` -- plaintext numbers (an int, a sequence or an integer array;
+        negatives allowed), which are encrypted first.  Returns ``[[x <= y]]`` as a ``BatchedPaillierCiphertext`` (``[B][2kN]``).
+
+        The session state (r, delta_A) stays on the device between the phases and every nonce not injected through ``nonces``
+        (keys ``r, rho_z, delta_a, r_blind, perm, rho_c``; parity runs) is drawn by the device CSPRNG; only the four protocol
+        messages cross PCIe.  Sessions of one ``Initiator`` may overlap (``asyncio.gather``): nothing of a session is kept on
+        ``self`` except the monotonically increasing ``session_id``."""
         if self.communicator is None:
             raise ValueError("Communicator not properly initialized.")
         self.session_id += 1
@@ -78,27 +92,20 @@ class Initiator:
         await self.receive_encryption_schemes(session_id)
         l = self.l_maximum_bit_length
         eng = get_engine(self.scheme_paillier, self.scheme_dgk, l)
-        nonces = nonces or {}
-        x_enc, y_enc = as_limbs(x, eng.kc), as_limbs(y, eng.kc)
-        B = x_enc.shape[0]
-        N = eng.paillier_n
-        r = nonces.get("r")
-        if r is None:
-            r = random_below(N, B, eng.kN)
-        rho_z = nonces.get("rho_z")
-        if rho_z is None:
-            rho_z = random_below(N, B, eng.kN, minimum=1)
-        from . import wire
-        out = (lambda a, kind: wire.pack(a, kind)) if self.wire_format else (lambda a, kind: a)
-        inp = (lambda m, kind: wire.unpack(m, kind) if isinstance(m, (bytes, bytearray, memoryview)) else m)
-        z_enc = eng.initiator_step1(x_enc, y_enc, r, rho_z, l)                      # step 1 + randomize
-        await self.communicator.send(self.other_party, out(z_enc, wire.KIND_PAILLIER_CT), msg_id=f"step_1_session_{session_id}")
-        db_enc = inp(await self.communicator.recv(self.other_party, msg_id=f"step_4b_session_{session_id}"), wire.KIND_DGK_VECTOR)
-        c_is_enc = self.steps_4c_to_4i(db_enc, r, l, self.scheme_dgk, self.scheme_paillier, delta_a=nonces.get("delta_a"),
-                                       r_blind=nonces.get("r_blind"), perm=nonces.get("perm"), rho=nonces.get("rho_c"), randomize=True)
-        await self.communicator.send(self.other_party, out(c_is_enc, wire.KIND_DGK_VECTOR), msg_id=f"step_4i_session_{session_id}")
-        enc3 = inp(await self.communicator.recv(self.other_party, msg_id=f"step_5_session_{session_id}"), wire.KIND_PAILLIER_TRIPLE)
-        return eng.initiator_step6_7(enc3, r, self._last_delta_a, l)               # steps 6 + 7
+        sess = InitiatorSession(eng, l, nonces, self.wire_format)
+        try:
+            z_msg = sess.phase_a1(x, y)                                                                   # step 1 + randomize
+            await self.communicator.send(self.other_party, z_msg, msg_id=f"step_1_session_{session_id}")
+            del z_msg
+            db_msg = await self.communicator.recv(self.other_party, msg_id=f"step_4b_session_{session_id}")
+            c_msg = sess.phase_a2(db_msg)                                                                 # steps 3, 4c-4i + randomize
+            del db_msg
+            await self.communicator.send(self.other_party, c_msg, msg_id=f"step_4i_session_{session_id}")
+            del c_msg
+            enc3_msg = await self.communicator.recv(self.other_party, msg_id=f"step_5_session_{session_id}")
+            return paillier_batch(sess.phase_a3(enc3_msg), self.scheme_paillier)                          # steps 6 + 7
+        finally:
+            sess.close()
 
     async def receive_encryption_schemes(self, session_id: int = 1) -> None:
         """Receive the schemes (public parts) from Bob and check them against pre-set ones
@@ -106,13 +113,12 @@ class Initiator:
         if self.communicator is None:
             raise ValueError("Communicator not properly initialized.")
         message = await self.communicator.recv(self.other_party, msg_id=f"schemes_session_{session_id}")
+        from . import wire
         if isinstance(message, (bytes, bytearray, memoryview)):
-            from . import wire
             received_paillier, received_dgk = wire.unpack_schemes(bytes(message))
-            differs = lambda mine, got: not wire.same_public_keys(mine, got)  # noqa: E731  (public parts travel, public parts compare)
         else:
             received_paillier, received_dgk = message
-            differs = lambda mine, got: mine != got  # noqa: E731  (the reference's scheme equality)
+        differs = lambda mine, got: not wire.same_public_keys(mine, got)  # noqa: E731  (public parts travel, public parts compare)
         if self._scheme_paillier is None:
             self._scheme_paillier = received_paillier
         elif differs(self.scheme_paillier, received_paillier):
@@ -145,9 +151,10 @@ class Initiator:
         eng = get_engine(scheme_paillier)
         x, y = as_limbs(x_enc, eng.kc), as_limbs(y_enc, eng.kc)
         if r is None:
-            r = random_below(N, x.shape[0], eng.kN)
+            eng.ensure_rng()
+            r = eng.rng_below(N, x.shape[0], eng.kN)
         r = as_limbs(r, eng.kN)
-        return eng.initiator_step1(x, y, r, None, l), r
+        return paillier_batch(eng.initiator_step1(x, y, r, None, l), scheme_paillier), r
 
     @staticmethod
     def step_3(r, l: int) -> np.ndarray:
@@ -165,13 +172,14 @@ class Initiator:
         d = as_limbs(d_enc, kn).copy()
         small = less_than_const(r, (N - 1) // 2)
         d[small] = int_to_limbs(1, kn)
-        return d
+        return dgk_batch(d, scheme_dgk)
 
     @staticmethod
     def step_4d(alpha, beta_is_enc, scheme_dgk=None) -> np.ndarray:
         """``[alpha_i xor beta_i]``: ``[beta_i]`` or ``g * [beta_i]^-1`` (initiator.py:293-328).
         (The reference finds the scheme on the ciphertext objects; limb arrays need it passed.)"""
-        eng = get_engine(None, _scheme_of(beta_is_enc, scheme_dgk))
+        eng_scheme = _scheme_of(beta_is_enc, scheme_dgk)
+        eng = get_engine(None, eng_scheme)
         alpha = _bits(alpha)
         beta = as_limbs(beta_is_enc, eng.kn)
         B, l, kn = beta.shape
@@ -179,12 +187,13 @@ class Initiator:
         inv = eng.modinv(nat.MOD_DGK_N, flat)
         g = np.broadcast_to(int_to_limbs(eng.dgk_g, kn), flat.shape)
         flipped = eng.modmul(nat.MOD_DGK_N, inv, np.ascontiguousarray(g))
-        return np.where(alpha.reshape(B * l, 1) != 0, flipped, flat).reshape(B, l, kn)
+        return dgk_batch(np.where(alpha.reshape(B * l, 1) != 0, flipped, flat).reshape(B, l, kn), eng_scheme)
 
     @staticmethod
     def step_4e(r, alpha, alpha_is_xor_beta_is_enc, d_enc, scheme_paillier, scheme_dgk=None) -> Tuple[np.ndarray, np.ndarray]:
         """``[w_i]`` and ``alpha~ = (r - N) mod 2^l`` (initiator.py:330-384)."""
-        eng = get_engine(None, _scheme_of(alpha_is_xor_beta_is_enc, scheme_dgk))
+        eng_scheme = _scheme_of(alpha_is_xor_beta_is_enc, scheme_dgk)
+        eng = get_engine(None, eng_scheme)
         N = int(scheme_paillier.public_key.n)
         r = np.ascontiguousarray(r, dtype=np.uint32)
         x = as_limbs(alpha_is_xor_beta_is_enc, eng.kn)
@@ -196,23 +205,24 @@ class Initiator:
         d_inv = eng.modinv(nat.MOD_DGK_N, d)
         with_d = eng.modmul(nat.MOD_DGK_N, x.reshape(B * l, kn), np.ascontiguousarray(np.repeat(d_inv, l, axis=0)))
         w = np.where((alpha != alpha_tilde).reshape(B * l, 1), with_d, x.reshape(B * l, kn)).reshape(B, l, kn)
-        return w, alpha_tilde
+        return dgk_batch(w, eng_scheme), alpha_tilde
 
     @staticmethod
     def step_4f(w_is_enc, scheme_dgk=None) -> np.ndarray:
         """``[w_i] <- [w_i]^(2^i) mod n`` (initiator.py:386-410)."""
-        eng = get_engine(None, _scheme_of(w_is_enc, scheme_dgk))
+        eng_scheme = _scheme_of(w_is_enc, scheme_dgk)
+        eng = get_engine(None, eng_scheme)
         w = as_limbs(w_is_enc, eng.kn)
         B, l, kn = w.shape
         ew = (l + 31) // 32 + 1
         exps = np.tile(ints_to_limbs([1 << i for i in range(l)], ew), (B, 1))
-        return eng.modexp(nat.MOD_DGK_N, w.reshape(B * l, kn), exps, exp_bits=l).reshape(B, l, kn)
+        return dgk_batch(eng.modexp(nat.MOD_DGK_N, w.reshape(B * l, kn), exps, exp_bits=l).reshape(B, l, kn), eng_scheme)
 
     @staticmethod
     def step_4g(batch: int = 1, delta_a: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
         """Uniform bits ``delta_A`` and ``s = 1 - 2 delta_A`` (initiator.py:412-421)."""
         if delta_a is None:
-            delta_a = np.array([secrets.randbelow(2) for _ in range(batch)], dtype=np.uint8)
+            delta_a = np.frombuffer(secrets.token_bytes(batch), dtype=np.uint8) & 1
         delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8)
         return 1 - 2 * delta_a.astype(np.int8), delta_a
 
@@ -249,7 +259,7 @@ class Initiator:
             out[:, i + 1] = mm(v, cube)
             w_sum = mm(w_sum, w[:, i])
         out[:, 0] = mm(w_sum, np.where((delta_a != 0)[:, None], int_to_limbs(g, kn)[None, :], one[None, :]))
-        return out
+        return dgk_batch(out, scheme_dgk)
 
     @staticmethod
     def step_4i(c_is_enc, scheme_dgk, do_shuffle: bool = True, r_blind: Optional[np.ndarray] = None,
@@ -261,15 +271,17 @@ class Initiator:
         u = int(scheme_dgk.public_key.u)
         rbw = (u.bit_length() + 31) // 32
         if r_blind is None:
-            r_blind = random_below(u, B * n_c, rbw, minimum=1).reshape(B, n_c, rbw)
+            eng.ensure_rng()
+            r_blind = eng.rng_below(u, B * n_c, rbw, min_one=True).reshape(B, n_c, rbw)
         r_blind = np.ascontiguousarray(r_blind, dtype=np.uint32).reshape(B * n_c, -1)
         masked = eng.modexp(nat.MOD_DGK_N, c.reshape(B * n_c, kn), r_blind, exp_bits=u.bit_length()).reshape(B, n_c, kn)
         if not do_shuffle:
-            return masked
+            return dgk_batch(masked, scheme_dgk)
         if perm is None:
-            perm = random_permutations(B, n_c)
+            eng.ensure_rng()
+            perm = eng.rng_permutations(n_c, B)
         perm = np.asarray(perm, dtype=np.int64)
-        return np.take_along_axis(masked, perm[:, :, None], axis=1)
+        return dgk_batch(np.take_along_axis(masked, perm[:, :, None], axis=1), scheme_dgk)
 
     @staticmethod
     def step_6(delta_a, delta_b_enc, scheme_paillier=None) -> np.ndarray:
@@ -280,7 +292,7 @@ class Initiator:
         inv = eng.modinv(nat.MOD_PAILLIER_N2, db)
         one_enc = np.tile(int_to_limbs(1 + eng.paillier_n, eng.kc), (db.shape[0], 1))
         flipped = eng.modmul(nat.MOD_PAILLIER_N2, inv, one_enc)
-        return np.where((delta_a == 1)[:, None], db, flipped)
+        return paillier_batch(np.where((delta_a == 1)[:, None], db, flipped), scheme_paillier if scheme_paillier is not None else getattr(delta_b_enc, 'scheme', None))
 
     @staticmethod
     def step_7(zeta_1_enc, zeta_2_enc, r, l: int, beta_lt_alpha_enc, scheme_paillier) -> np.ndarray:
@@ -292,33 +304,35 @@ class Initiator:
         zeta = np.where(less_than_const(r, (N - 1) // 2)[:, None], z1, z2)
         r_div = eng.paillier_encrypt(shift_right(r, l))
         t = eng.modmul(nat.MOD_PAILLIER_N2, r_div, as_limbs(beta_lt_alpha_enc, eng.kc))
-        return eng.modmul(nat.MOD_PAILLIER_N2, np.ascontiguousarray(zeta), eng.modinv(nat.MOD_PAILLIER_N2, t))
+        return paillier_batch(eng.modmul(nat.MOD_PAILLIER_N2, np.ascontiguousarray(zeta), eng.modinv(nat.MOD_PAILLIER_N2, t)), scheme_paillier)
 
     # ------------------------------------------------------------------ fused phases
-    def steps_4c_to_4i(self, db_enc, r, l: int, scheme_dgk, scheme_paillier, delta_a=None, r_blind=None, perm=None, rho=None,
-                       randomize: bool = True, do_shuffle: bool = True) -> np.ndarray:
-        """Steps 3, 4c-4i (+ ``randomize()`` of every ``[c_i]``, initiator.py:153-154) in one device pass.
-        ``db_enc``: ``[B][l+1][kn]`` (``[d]`` then ``[beta_i]``) as produced by ``KeyHolder.steps_4a_4b``."""
+    @staticmethod
+    def steps_4c_to_4i(db_enc, r, l: int, scheme_dgk, scheme_paillier, delta_a, r_blind=None, perm=None, rho=None,
+                       randomize: bool = True, do_shuffle: bool = True) -> BatchedDGKCiphertext:
+        """Steps 3, 4c-4f, 4h, 4i (+ ``randomize()`` of every ``[c_i]``, initiator.py:153-154) in one device pass.
+        ``db_enc``: ``[B][l+1][kn]`` (``[d]`` then ``[beta_i]``) as produced by ``KeyHolder.steps_4a_4b``; ``delta_a``: the ``[B]`` coins
+        of ``step_4g`` (drawn by the caller, as in the reference flow, and needed again by ``steps_6_7``).  The other nonces
+        default to the device CSPRNG; pass arrays to inject them (parity runs)."""
         eng = get_engine(scheme_paillier, scheme_dgk, l)
-        db = np.ascontiguousarray(db_enc, dtype=np.uint32)
+        db = as_limbs(db_enc, eng.kn)
         B = db.shape[0]
         r = np.ascontiguousarray(r, dtype=np.uint32)
         assert bool(np.all(less_than_const(r, eng.paillier_n)))
-        _, delta_a = Initiator.step_4g(B, delta_a)
-        self._last_delta_a = delta_a
-        u = eng.u
+        delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8).reshape(B)
+        eng.ensure_rng()
         if r_blind is None:
-            r_blind = random_below(u, B * (l + 1), eng.rb_words, minimum=1).reshape(B, l + 1, eng.rb_words)
+            r_blind = eng.rng_below(eng.u, B * (l + 1), eng.rb_words, min_one=True).reshape(B, l + 1, eng.rb_words)
         if perm is None and do_shuffle:
-            perm = random_permutations(B, l + 1)
+            perm = eng.rng_permutations(l + 1, B)
         if rho is None and randomize:
-            bits = eng._fixed_base[0][1]
-            rho = random_bits(bits, B * (l + 1), eng.rand_words).reshape(B, l + 1, eng.rand_words)
-        return eng.initiator_step4(db, r, delta_a, r_blind, perm if do_shuffle else None, rho if randomize else None, l)
+            rho = eng.rng_bits(eng._fixed_base[0][1], B * (l + 1), eng.rand_words).reshape(B, l + 1, eng.rand_words)
+        c = eng.initiator_step4(db, r, delta_a, r_blind, perm if do_shuffle else None, rho if randomize else None, l)
+        return dgk_batch(c, scheme_dgk, fresh=randomize)
 
     @staticmethod
-    def steps_6_7(enc3, r, delta_a, l: int, scheme_paillier) -> np.ndarray:
+    def steps_6_7(enc3, r, delta_a, l: int, scheme_paillier) -> BatchedPaillierCiphertext:
         """Steps 6 and 7 fused: ``enc3`` = ``[B][3][2kN]`` (``[[zeta_1]], [[zeta_2]], [[delta_B]]``)."""
         eng = get_engine(scheme_paillier)
-        return eng.initiator_step6_7(np.ascontiguousarray(enc3, dtype=np.uint32), np.ascontiguousarray(r, dtype=np.uint32),
-                                     np.ascontiguousarray(delta_a, dtype=np.uint8), l)
+        return paillier_batch(eng.initiator_step6_7(np.ascontiguousarray(enc3, dtype=np.uint32), np.ascontiguousarray(r, dtype=np.uint32),
+                                                    np.ascontiguousarray(delta_a, dtype=np.uint8), l), scheme_paillier)

@@ -48,12 +48,12 @@ def _paillier_primes(sk, n: int, lam: int):
 
 
 def as_limbs(values, k: int) -> np.ndarray:
-    """Batch container -> ``[..][k]`` uint32 limbs.  Accepts limb arrays (returned as is), a single
-    ciphertext / int (batch of one), or (nested) sequences of ciphertexts / ints."""
+    """Batch container -> ``[..][k]`` uint32 limbs.  Accepts batched ciphertext containers (``ciphertexts.py``), limb
+    arrays (returned as is), a single scheme ciphertext / raw int (batch of one), or (nested) sequences of those."""
     if isinstance(values, np.ndarray) and values.dtype == np.uint32:
         if values.shape[-1] != k:
             raise ValueError(f"limb arrays for this modulus need {k} limbs per value, got {values.shape[-1]}")
-        return np.ascontiguousarray(values)
+        return np.ascontiguousarray(values)          # (containers are uint32 ndarray subclasses: this drops the wrapper)
     if isinstance(values, (int, np.integer)) or hasattr(values, "peek_value"):
         return ints_to_limbs([_raw(values)], k)
     if isinstance(values, np.ndarray):
@@ -62,6 +62,25 @@ def as_limbs(values, k: int) -> np.ndarray:
     if values and isinstance(values[0], (list, tuple, np.ndarray)):
         return np.stack([as_limbs(v, k) for v in values])
     return ints_to_limbs([_raw(v) for v in values], k)
+
+
+def is_ciphertext_batch(values) -> bool:
+    """True for what the drivers treat as ENCRYPTED input (batched containers, uint32 limb arrays, scheme ciphertext objects or
+    sequences of them); everything else numeric is a plaintext to encrypt first (reference ``initiator.py:93-102``)."""
+    from .ciphertexts import BatchedCiphertext
+    if isinstance(values, BatchedCiphertext) or hasattr(values, "peek_value"):
+        return True
+    if isinstance(values, np.ndarray):
+        return values.dtype == np.uint32 and values.ndim >= 2
+    if isinstance(values, (list, tuple)) and values:
+        return is_ciphertext_batch(values[0])
+    return False
+
+
+def _check_shape(name: str, arr: np.ndarray, shape) -> np.ndarray:
+    if tuple(arr.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(arr.shape)}")
+    return arr
 
 
 def _dgk_raw_of_minus_one(dgk) -> Optional[int]:
@@ -97,6 +116,37 @@ class SchemeEngine(Engine):
         self.has_paillier_secret = False
         self.has_paillier_crt = False
         self.has_dgk_secret = False
+        from .device import BufferPool
+        self.pool = BufferPool(self)
+        self._rng_seeded = False
+
+    def close(self) -> None:
+        if getattr(self, "pool", None) is not None:
+            self.pool.close()
+        super().close()
+
+    def rng_seed(self, key=None, nonce=None) -> None:
+        super().rng_seed(key, nonce)
+        self._rng_seeded = True
+
+    def ensure_rng(self) -> None:
+        """Key the device CSPRNG from ``secrets`` once (the drivers draw every nonce on the device by default)."""
+        if not self._rng_seeded:
+            self.rng_seed()
+
+    def encode_paillier_plain(self, values) -> np.ndarray:
+        """Plaintext integers -> ``[B][kN]`` limbs of the Paillier plaintext space: the integer encoding of the reference's
+        ``scheme.unsafe_encrypt(x)`` (negative values wrap modulo N, ``test_secure_comparison.py:27-37`` uses -400, -1)."""
+        N = self.paillier_n
+        flat = np.asarray(values, dtype=object).reshape(-1)
+        out = []
+        for v in flat:
+            if isinstance(v, (float, np.floating)):
+                if not float(v).is_integer():
+                    raise ValueError("only integral plaintexts can be compared")
+                v = int(v)
+            out.append(int(v) % N)
+        return ints_to_limbs(out, self.kN)
 
     # ------------------------------------------------------------------ keys
     def load_paillier(self, scheme) -> None:
@@ -172,6 +222,8 @@ class SchemeEngine(Engine):
     def paillier_encrypt(self, plain: np.ndarray, rho: Optional[np.ndarray] = None) -> np.ndarray:
         """``(1 + m N) * rho^N mod N^2`` -- ``unsafe_encrypt(m, apply_encoding=False)`` [+ ``randomize()``]."""
         plain = nat._host_u32(plain)
+        if plain.ndim < 1 or plain.shape[-1] != self.kN:
+            raise ValueError(f"plaintexts must be [..][{self.kN}] limbs")
         shape = plain.shape[:-1]
         M = int(np.prod(shape)) if shape else 1
         rho_a = None if rho is None else nat._host_u32(rho, plain.shape)
@@ -182,6 +234,8 @@ class SchemeEngine(Engine):
     def paillier_decrypt(self, c: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Raw plaintext in ``[0, N)`` -- ``decrypt(c, apply_encoding=False)``."""
         c = nat._host_u32(c)
+        if c.ndim < 1 or c.shape[-1] != self.kc:
+            raise ValueError(f"Paillier ciphertexts must be [..][{self.kc}] limbs")
         shape = c.shape[:-1]
         M = int(np.prod(shape)) if shape else 1
         out = _out(out, shape + (self.kN,))
@@ -190,6 +244,8 @@ class SchemeEngine(Engine):
 
     def dgk_is_zero(self, c: np.ndarray) -> np.ndarray:
         c = nat._host_u32(c)
+        if c.ndim < 1 or c.shape[-1] != self.kn:
+            raise ValueError(f"DGK ciphertexts must be [..][{self.kn}] limbs")
         shape = c.shape[:-1]
         M = int(np.prod(shape)) if shape else 1
         flags = np.zeros(shape, dtype=np.uint8)
@@ -201,6 +257,7 @@ class SchemeEngine(Engine):
                         out: Optional[np.ndarray] = None) -> np.ndarray:
         x = nat._host_u32(x)
         B = x.shape[0]
+        _check_shape("x", x, (B, self.kc))
         y = nat._host_u32(y, (B, self.kc))
         r = nat._host_u32(r, (B, self.kN))
         rho_a = None if rho is None else nat._host_u32(rho, (B, self.kN))
@@ -211,10 +268,11 @@ class SchemeEngine(Engine):
     def keyholder_step4ab(self, z: np.ndarray, l: int, rho: Optional[np.ndarray], out: Optional[np.ndarray] = None) -> np.ndarray:
         z = nat._host_u32(z)
         B = z.shape[0]
+        _check_shape("z", z, (B, self.kN))
         rho_a, rw = None, 0
         if rho is not None:
             rho_a = nat._host_u32(rho)
-            if rho_a.shape[:2] != (B, l + 1):
+            if rho_a.ndim != 3 or rho_a.shape[:2] != (B, l + 1):
                 raise ValueError("rho must be [B][l+1][words]")
             rw = rho_a.shape[2]
         out = _out(out, (B, l + 1, self.kn))
@@ -232,13 +290,15 @@ class SchemeEngine(Engine):
         rb, rbw = None, 0
         if r_blind is not None:
             rb = nat._host_u32(r_blind)
-            if rb.shape[:2] != (B, l + 1):
+            if rb.ndim != 3 or rb.shape[:2] != (B, l + 1):
                 raise ValueError("r_blind must be [B][l+1][words]")
             rbw = rb.shape[2]
         pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.uint8).reshape(B, l + 1)
         rho_a, rw = None, 0
         if rho is not None:
             rho_a = nat._host_u32(rho)
+            if rho_a.ndim != 3 or rho_a.shape[:2] != (B, l + 1):
+                raise ValueError("rho must be [B][l+1][words]")
             rw = rho_a.shape[2]
         out = _out(out, (B, l + 1, self.kn))
         self._check(self.lib.scb_initiator_step4(self.ctx, nat._ptr(db_enc), nat._ptr(r), nat._ptr(delta_a), nat._ptr(rb), rbw, nat._ptr(pm),
@@ -249,6 +309,7 @@ class SchemeEngine(Engine):
                            out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
         c = nat._host_u32(c)
         B = c.shape[0]
+        _check_shape("c_is_enc", c, (B, l + 1, self.kn))
         z = nat._host_u32(z, (B, self.kN))
         rho_a = None if rho is None else nat._host_u32(rho, (B, 3, self.kN))
         delta_b = _out(None if out is None else out[0], (B,), np.uint8)
@@ -259,6 +320,7 @@ class SchemeEngine(Engine):
     def keyholder_step5(self, z: np.ndarray, delta_b: np.ndarray, rho: Optional[np.ndarray], l: int) -> np.ndarray:
         z = nat._host_u32(z)
         B = z.shape[0]
+        _check_shape("z", z, (B, self.kN))
         delta_b = np.ascontiguousarray(delta_b, dtype=np.uint8).reshape(B)
         rho_a = None if rho is None else nat._host_u32(rho, (B, 3, self.kN))
         enc3 = np.empty((B, 3, self.kc), dtype=np.uint32)
@@ -268,6 +330,7 @@ class SchemeEngine(Engine):
     def initiator_step6_7(self, enc3: np.ndarray, r: np.ndarray, delta_a: np.ndarray, l: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         enc3 = nat._host_u32(enc3)
         B = enc3.shape[0]
+        _check_shape("enc3", enc3, (B, 3, self.kc))
         r = nat._host_u32(r, (B, self.kN))
         delta_a = np.ascontiguousarray(delta_a, dtype=np.uint8).reshape(B)
         out = _out(out, (B, self.kc))
@@ -275,14 +338,47 @@ class SchemeEngine(Engine):
         return out
 
 
+    # ------------------------------------------------------------------ fused phases (device buffers: anything with data_ptr())
+    def initiator_step1_dev(self, x, y, r, rho, l: int, out, B: int) -> None:
+        self._check(self.lib.scb_initiator_step1_dev(self.ctx, nat._ptr(x), nat._ptr(y), nat._ptr(r), nat._ptr(rho), l, nat._ptr(out), B))
+
+    def paillier_encrypt_dev(self, plain, rho, out, M: int) -> None:
+        self._check(self.lib.scb_paillier_encrypt_dev(self.ctx, nat._ptr(plain), nat._ptr(rho), nat._ptr(out), M))
+
+    def paillier_decrypt_dev(self, c, out, M: int) -> None:
+        self._check(self.lib.scb_paillier_decrypt_dev(self.ctx, nat._ptr(c), nat._ptr(out), M))
+
+    def keyholder_step4ab_dev(self, z, l: int, rho, rho_words: int, out, B: int) -> None:
+        self._check(self.lib.scb_keyholder_step4ab_dev(self.ctx, nat._ptr(z), l, nat._ptr(rho), rho_words, nat._ptr(out), B))
+
+    def initiator_step4_dev(self, db_enc, r, delta_a, r_blind, rb_words: int, perm, rho, rho_words: int, l: int, out, B: int) -> None:
+        self._check(self.lib.scb_initiator_step4_dev(self.ctx, nat._ptr(db_enc), nat._ptr(r), nat._ptr(delta_a), nat._ptr(r_blind), rb_words,
+                                                     nat._ptr(perm), nat._ptr(rho), rho_words, l, nat._ptr(out), B))
+
+    def keyholder_step4j_5_dev(self, c, z, rho, l: int, delta_b, enc3, B: int) -> None:
+        self._check(self.lib.scb_keyholder_step4j_5_dev(self.ctx, nat._ptr(c), nat._ptr(z), nat._ptr(rho), l, nat._ptr(delta_b), nat._ptr(enc3), B))
+
+    def initiator_step6_7_dev(self, enc3, r, delta_a, l: int, out, B: int) -> None:
+        self._check(self.lib.scb_initiator_step6_7_dev(self.ctx, nat._ptr(enc3), nat._ptr(r), nat._ptr(delta_a), l, nat._ptr(out), B))
+
+
 # -------------------------------------------------------------------------------------------------
 # engine registry: the reference's step functions are static methods that only receive scheme objects,
 # so the batched mirror looks the engine up from the schemes it is given.
 # -------------------------------------------------------------------------------------------------
 _ENGINES: dict = {}
+_DEFAULT_DEVICE = 0
 
 
-def get_engine(scheme_paillier=None, scheme_dgk=None, l: Optional[int] = None, device: int = 0) -> SchemeEngine:
+def set_default_device(device: int) -> None:
+    """CUDA device ordinal the scheme-driven API (``Initiator`` / ``KeyHolder`` steps and drivers, ciphertext containers) runs
+    on in this process -- one process per GPU sets it to its local rank."""
+    global _DEFAULT_DEVICE
+    _DEFAULT_DEVICE = int(device)
+
+
+def get_engine(scheme_paillier=None, scheme_dgk=None, l: Optional[int] = None, device: Optional[int] = None) -> SchemeEngine:
+    device = _DEFAULT_DEVICE if device is None else device
     eng = _ENGINES.get(device)
     if eng is None:
         eng = _ENGINES[device] = SchemeEngine(device)

@@ -36,6 +36,30 @@ def pack(array: np.ndarray, kind: int = KIND_GENERIC) -> bytes:
     return header + a.astype(dt, copy=False).tobytes()
 
 
+def header(kind: int, dtype, shape) -> bytes:
+    """The SCB1 header of an array message; ``len(header) + payload bytes`` is the blob size."""
+    dt = np.dtype(dtype)
+    dt = dt.newbyteorder("<") if dt.itemsize > 1 else dt
+    if dt not in _CODES:
+        raise TypeError(f"unsupported dtype {dtype}")
+    if len(shape) > 8:
+        raise ValueError("too many dimensions")
+    return MAGIC + struct.pack("<BBBB", kind, _CODES[dt], len(shape), 0) + struct.pack(f"<{len(shape)}I", *shape)
+
+
+def blob_with_payload_view(alloc, kind: int, shape, dtype=np.uint32):
+    """Build a message IN PLACE: ``alloc(nbytes)`` returns a writable uint8 array (e.g. pinned host memory); the header is
+    written at its start and the returned ``payload`` is a ``shape`` / ``dtype`` view of the rest, to be filled by the caller
+    (a device-to-host copy lands directly in the message, no intermediate array).  Returns ``(blob_memoryview, payload)``."""
+    head = header(kind, dtype, shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    blob = alloc(len(head) + nbytes)
+    blob[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+    payload = blob[len(head):len(head) + nbytes].view(dt).reshape(shape)
+    return memoryview(blob)[:len(head) + nbytes], payload
+
+
 def unpack(blob: bytes, expect_kind: int | None = None) -> np.ndarray:
     if len(blob) < 8 or blob[:4] != MAGIC:
         raise ValueError("not an SCB1 message")
@@ -80,6 +104,12 @@ def unpack_schemes(blob: bytes) -> Tuple[SimpleNamespace, SimpleNamespace]:
     paillier = SimpleNamespace(public_key=SimpleNamespace(n=pn, n_squared=pn * pn, g=pn + 1), secret_key=None)
     dgk = SimpleNamespace(public_key=SimpleNamespace(n=dn, g=g, h=h, u=u, t=t), secret_key=None, randomness_bits=(5 * t) // 2)
     return paillier, dgk
+
+
+def public_only(scheme_paillier, scheme_dgk) -> Tuple[SimpleNamespace, SimpleNamespace]:
+    """Fresh holders carrying ONLY the public parts of both schemes (what ``unpack_schemes`` would rebuild on the other
+    side).  The KeyHolder sends these -- never the scheme objects themselves, which carry the secret keys."""
+    return unpack_schemes(pack_schemes(scheme_paillier, scheme_dgk))
 
 
 def same_public_keys(a, b) -> bool:

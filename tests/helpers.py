@@ -115,35 +115,6 @@ def run_device_pass(eng, paillier, dgk, l, x, y):
 
 
 # ---------------------------------------------------------------------------------------------
-# oracle transcripts on all host cores (the oracle needs ~56 ms per 2048-bit comparison on one core)
+# oracle transcripts on all host cores: oracle/parallel.py (shared with bench.py's parity gate)
 # ---------------------------------------------------------------------------------------------
-def _oracle_worker(args):
-    key_spec, l, chunk = args
-    from oracle.protocol import Nonces, Oracle
-    from oracle.workload import make_schemes
-    paillier, dgk = make_schemes(*key_spec)
-    oracle = Oracle(paillier, dgk, "auto")
-    out = []
-    for x_enc, y_enc, nonce_fields in chunk:
-        t = oracle.compare(x_enc, y_enc, l, Nonces(**nonce_fields), interactive=True, decrypt_result=False)
-        out.append((t.z_enc, t.z, [t.d_enc_sent] + list(t.beta_enc_sent), list(t.c_enc_sent), t.delta_b,
-                    (t.zeta1_sent, t.zeta2_sent, t.delta_b_sent), t.result_enc))
-    return out
-
-
-def oracle_transcripts_parallel(key_spec, l, cases, processes=None):
-    """[(z_enc, z, db_sent[l+1], c_sent[l+1], delta_b, enc3, result_enc)] for every case, computed in `processes` workers
-    (spawned, so no CUDA state is inherited)."""
-    import dataclasses
-    import multiprocessing as mp
-    import os
-    processes = processes or min(len(cases), os.cpu_count() or 1)
-    items = [(c["x_enc"], c["y_enc"], dataclasses.asdict(c["nonces"])) for c in cases]
-    chunks = [items[i::processes] for i in range(processes)]
-    with mp.get_context("spawn").Pool(processes) as pool:
-        parts = pool.map(_oracle_worker, [(key_spec, l, ch) for ch in chunks])
-    out = [None] * len(items)
-    for p, part in enumerate(parts):
-        for j, t in enumerate(part):
-            out[p + j * processes] = t
-    return out
+from oracle.parallel import oracle_transcripts_parallel  # noqa: E402,F401

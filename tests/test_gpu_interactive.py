@@ -49,7 +49,8 @@ def test_interactive_batch_matches_oracle(wire_format):
     assert limbs_to_ints(result) == [t.result_enc for t in ts]
     assert limbs_to_ints(eng.paillier_decrypt(result)) == [int(x <= y) for x, y in pairs]
     assert [m for m, _, _ in log] == ["schemes_session_1", "step_1_session_1", "step_4b_session_1", "step_4i_session_1", "step_5_session_1"]
-    assert all((kind == "bytes") == wire_format for _, kind, _ in log)
+    assert all((kind in ("bytes", "memoryview")) == wire_format for _, kind, _ in log)
+    assert all(size > 0 for _, _, size in log[1:])
     assert alice.scheme_paillier.public_key.n == paillier.public_key.n and getattr(alice.scheme_paillier, "secret_key", None) is None
 
 
@@ -83,3 +84,89 @@ def test_two_sessions_and_scheme_mismatch():
 
     with pytest.raises(ValueError):
         asyncio.run(mismatch())
+
+
+def _big_keys():
+    from bench import key_file
+    from protocols.secure_comparison_b200.keyfile import schemes_from_json
+    return schemes_from_json(key_file(2048, 2048, 16))
+
+
+def test_unencrypted_inputs_are_encrypted_first():
+    """``perform_secure_comparison(x, y)`` with plaintext numbers, negatives included (reference initiator.py:93-102,
+    test_secure_comparison.py:27-37, 776-800), at Paillier-2048 / DGK-2048; also one side encrypted, one side plain."""
+    l = 16
+    paillier, dgk = _big_keys()
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    pairs = [(-400, -383), (-1, 0), (0, 2), (1, 10), (230, 269), (1508, 2408), (3122, 6048), (4250, 7804), (8668, 9015), (7, 7), (9015, 8668), (0, -1)]
+    xs, ys = [p[0] for p in pairs], [p[1] for p in pairs]
+    store = {}
+    alice = Initiator(l, DictionaryCommunicator(store, None), "bob", wire_format=True)
+    bob = KeyHolder(l, DictionaryCommunicator(store, None), "alice", scheme_paillier=paillier, scheme_dgk=dgk, wire_format=True)
+
+    async def run(x, y):
+        return (await asyncio.gather(alice.perform_secure_comparison(x, y), bob.perform_secure_comparison()))[0]
+
+    want = [int(x <= y) for x, y in pairs]
+    assert limbs_to_ints(eng.paillier_decrypt(asyncio.run(run(xs, ys)))) == want
+    y_enc = eng.paillier_encrypt(eng.encode_paillier_plain(ys))
+    assert limbs_to_ints(eng.paillier_decrypt(asyncio.run(run(np.array(xs), y_enc)))) == want
+    assert limbs_to_ints(eng.paillier_decrypt(asyncio.run(run(23, 42)))) == [1]          # the README example, scalars
+
+
+def test_parallel_runs_on_one_player_pair():
+    """Two sessions in flight on ONE Initiator / KeyHolder pair (reference test_secure_comparison.py:803-835), different batch
+    sizes, device-drawn nonces: nothing of a session may live on the player objects."""
+    l = 16
+    paillier, dgk = _big_keys()
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    store = {}
+    alice = Initiator(l, DictionaryCommunicator(store, None), "bob")
+    bob = KeyHolder(l, DictionaryCommunicator(store, None), "alice", scheme_paillier=paillier, scheme_dgk=dgk)
+    rng = random.Random(5)
+    x1, y1 = [rng.randrange(1 << l) for _ in range(40)], [rng.randrange(1 << l) for _ in range(40)]
+    x2, y2 = [11, 41, 12], [12, 41, 11]
+
+    async def both():
+        tasks = [asyncio.create_task(alice.perform_secure_comparison(x1, y1)), asyncio.create_task(alice.perform_secure_comparison(x2, y2)),
+                 asyncio.create_task(bob.perform_secure_comparison()), asyncio.create_task(bob.perform_secure_comparison())]
+        return await asyncio.gather(*tasks)
+
+    r1, r2, _, _ = asyncio.run(both())
+    assert limbs_to_ints(eng.paillier_decrypt(r1)) == [int(a <= b) for a, b in zip(x1, y1)]
+    assert limbs_to_ints(eng.paillier_decrypt(r2)) == [1, 1, 0]
+    assert alice.session_id == bob.session_id == 2
+
+
+def test_malformed_messages_are_rejected_before_any_copy():
+    """A message whose shape does not fit the session (the other party controls it) raises ValueError instead of making the
+    library read past the end of the buffer."""
+    from protocols.secure_comparison_b200 import wire
+    from protocols.secure_comparison_b200.sessions import InitiatorSession, KeyHolderSession
+    l = 16
+    paillier, dgk = make_schemes(1024, 128, 20, l)
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    a = InitiatorSession(eng, l, None, False)
+    a.phase_a1([1, 2, 3], [3, 2, 1])
+    short = np.zeros((2, l + 1, eng.kn), dtype=np.uint32)
+    with pytest.raises(ValueError):
+        a.phase_a2(short)
+    with pytest.raises(ValueError):
+        a.phase_a2(wire.pack(short, wire.KIND_DGK_VECTOR))
+    with pytest.raises(ValueError):
+        a.phase_a2(np.zeros((3, l + 1, eng.kn), dtype=np.uint64))
+    a.close()
+    b = KeyHolderSession(eng, l, None, False)
+    with pytest.raises(ValueError):
+        b.phase_b1(np.zeros((3, eng.kc - 1), dtype=np.uint32))
+    b.phase_b1(np.ones((3, eng.kc), dtype=np.uint32))
+    with pytest.raises(ValueError):
+        b.phase_b2(np.zeros((3, l, eng.kn), dtype=np.uint32))
+    b.close()
+    with pytest.raises(ValueError):
+        eng.initiator_step6_7(np.zeros((3, 2, eng.kc), dtype=np.uint32), np.zeros((3, eng.kN), dtype=np.uint32), np.zeros(3, dtype=np.uint8), l)
+    with pytest.raises(ValueError):
+        eng.keyholder_step4j_5(np.zeros((3, l, eng.kn), dtype=np.uint32), np.zeros((3, eng.kN), dtype=np.uint32), None, l)

@@ -10,7 +10,7 @@ from protocols.secure_comparison_b200.keyfile import schemes_from_json
 from protocols.secure_comparison_b200.pipeline import LocalPipeline
 
 B, l = int(sys.argv[1]) if len(sys.argv) > 1 else 65536, 16
-paillier, dgk = schemes_from_json(bench.KEY_FILE)
+paillier, dgk = schemes_from_json(bench.key_file(2048, 2048, 16))
 eng = SchemeEngine(0); eng.load_paillier(paillier); eng.load_dgk(dgk, l)
 w, truth = bench.make_workload(B, l, 7, eng)
 h = {k: torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory().numpy() for k, v in w.items()}
