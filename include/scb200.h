@@ -164,6 +164,8 @@ enum {
                                    FP64 engine (default 1; 0 = fixed windows everywhere) */
   SCB_OPT_MODEXP_FP64 = 3,      /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
                                    the IMAD one (default 1; results are bit-identical either way) */
+  SCB_OPT_SMALL_BATCH = 6,      /* FP64 engine: batches that cannot fill half of the GPU's resident groups run with 5 digits per lane on
+                                   twice as many lanes per number (default 1; results are bit-identical either way) */
   SCB_OPT_SQUARE_MODULUS = 5    /* exponentiations modulo a linked square n^2 (N^2, p^2, q^2: scb_modulus_link_square) in base-n pair
                                    form on the FP64 engine: half the digit products of a plain product mod n^2 (default 1; 0 = treat
                                    n^2 as an ordinary modulus; results are bit-identical either way) */

@@ -55,7 +55,7 @@ struct Geo52 {
   static_assert(32 % TPI == 0, "TPI must divide the warp");
   static constexpr int K = L * TPI;
   static constexpr int GPW = 32 / TPI;
-  static constexpr int WARP_SMEM_DOUBLES = (K + 2) * GPW;   // +2 zero rows: the row loop multiplies by b[j+1] and loads b[j+2] one row ahead
+  static constexpr int WARP_SMEM_DOUBLES = (K + 1) * GPW;   // +1 row: the row loop prefetches b[j+1]
 };
 
 __device__ __forceinline__ double u52_to_double(uint64_t v) { return __longlong_as_double(static_cast<long long>(v | BITS_2P52)) - SCB_2P52; }
@@ -107,32 +107,24 @@ __device__ __forceinline__ void resolve_carries(uint64_t (&col)[L], uint64_t hi_
 }
 
 // ---- the row loop -------------------------------------------------------------------------------------------------
-// One exact 52 x 52 -> 104-bit product in the mantissas of two doubles, added as raw bit patterns into a column pair.
-#define SCB_PROD_HI(x, y) __fma_rz((x), (y), C1)
-#define SCB_PROD_LO(x, y, hi) __fma_rz((x), (y), __dsub_rn(C12, (hi)))
-
 constexpr int PASS_SAVE = 1;     // store the complemented quotient digits of this pass (pair arithmetic, pass 1)
 constexpr int PASS_INJECT = 2;   // add the stored complement (+1) into the low column of every row (pair arithmetic, pass 2)
 
 // The row loop of one Montgomery product on register operands, returning the UNRESOLVED columns:
 //   sum_p col[p] 2^(52 p) + hi_last 2^(52 L)  (per lane)  =  this lane's share of (a * b [+ R - m] + q n) / R
 //   av[L], nv[L] : this lane's digits of a and of the modulus; b is ALREADY staged in shared memory (digit j at
-//   sm_stream[j * GPW], made visible with __syncwarp() by stage_digits52()); rows K and K+1 of the area must hold 0.0
-//   (zero_pad_rows52(), once per kernel) because the loop multiplies by b[j+1] and loads b[j+2] one row ahead.
+//   sm_stream[j * GPW], made visible with __syncwarp() by stage_digits52(); the pad row K may hold anything).
 //   PAIR: the two hooks of the square-modulus arithmetic (kernels_f64_pair.cuh); flags is warp-uniform.
-//
-// Schedule (model with the same data flow and constants: tests/mmd52_model.py).  The quotient digit is a serial chain
-// through every row -- column 0 -> q = lo(col0 * n') -> SHFL -> n_0 q, n_1 q -> carry into column 1 = the next column 0 --
-// about a dozen dependent operations, and the two passes of a warp over an unrolled row used to run it with nothing else
-// in flight (ncu: "wait" stalls on exactly those instructions, FP64 pipe 47-62 % busy).  Here the chain is interleaved, in
-// SOURCE order (ptxas keeps it), with the work that does not depend on it: the products n_i q of the PREVIOUS row for
-// i >= 2, the products a_i b_j of this row, and a_0 b_{j+1}, which is computed one row early so that column 1 is complete
-// -- and the next chain can start -- as soon as n_0 q and n_1 q have landed.
 // All 32 lanes of the warp must call this together.
+//
+// What bounds it (tools/rowloop_microbench.cu, profiles/r02_rowloop_microbench.jsonl): the FP64 pipe's issue rate for this
+// instruction mix, not latency -- 211-215 cycles per warp-row and scheduler whether 1, 2, 3 or 4 blocks are resident per SM.
+// Breaking the serial quotient chain on purpose buys 9 %, dropping the shuffles 4 %, replacing the 64-bit adds nothing; a
+// software-pipelined variant of this loop (a_0 b_{j+1} one row early, products of the previous row's quotient digit inside
+// the next chain, accumulation delayed by one product pair) measured the same 215 cycles, so the plain form stays.
 template <int L, int TPI, bool PAIR>
 __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const double (&nv)[L], const double np, const double* __restrict__ sm_stream,
                                               uint64_t* __restrict__ sm_q, const int flags, uint64_t (&col)[L], uint64_t& hi_last) {
-  static_assert(L >= 6, "the interleaved schedule places products 1..5 by hand");
   constexpr int GPW = Geo52<L, TPI>::GPW;
   const int t = (threadIdx.x & 31) % TPI;
   const bool top = t == TPI - 1;
@@ -148,145 +140,83 @@ __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const doubl
     AL[i] = 0ull - 2ull * (i + 1) * BITS_2P52;
     AH[i] = 0ull - 2ull * (i + 1) * BITS_2P104;
   }
+  if (PAIR && inject && low_lane) AL[0] += 1ull;           // the "+ 1" of R - m = complement(m) + 1
   const double* bp = sm_stream;
-  const uint64_t* qin = sm_q;
-  uint64_t* qout = sm_q;
-  double b0 = bp[0], b1 = bp[GPW];
-  {
-    // prologue: a_0 b_0 (every later row finds its a_0 b_j already in place), first complement digit + 1
-    const double hi = SCB_PROD_HI(av[0], b0);
-    const double lo = SCB_PROD_LO(av[0], b0, hi);
-    AH[0] += raw(hi);
-    AL[0] += raw(lo);
-    if (PAIR && inject && low_lane) AL[0] += qin[0] + 1ull;
-  }
-  double qprev = 0.0;                                     // quotient digit of the previous row (its n_i q for i >= 2 are still owed)
+  uint64_t* qp = sm_q;
+  double bj = bp[0];
 #pragma unroll 1
   for (int blk = 0; blk < TPI; blk++) {
 #pragma unroll
     for (int rr = 0; rr < L; rr++) {
       // logical column i of this row lives in AL/AH[(i + rr) % L]
-#define COL(i) (((i) + rr) % L)
-#define OWED(i) (((i) + rr - 1 + L) % L)                  /* column i of the PREVIOUS row */
       bp += GPW;
-      const double b2 = bp[GPW];                           // b[j+2]
-      uint64_t cnext = 0ull;
-      if (PAIR && inject) cnext = qin[GPW];                // complement digit j+1 (row K of the area holds 0)
-      qin += GPW;
-      // ---- chain A, step 1: column 0 -> double
-      const double v0 = u52_to_double(AL[COL(0)] & MASK52);
-      // owed from the previous row: n_i qprev, i = 2, 3 (none in the first row of a block: they were paid before the back-edge)
-      if (rr > 0) {
-        const double h2 = SCB_PROD_HI(nv[2], qprev), h3 = SCB_PROD_HI(nv[3], qprev);
-        const double l2 = SCB_PROD_LO(nv[2], qprev, h2), l3 = SCB_PROD_LO(nv[3], qprev, h3);
-        AH[OWED(2)] += raw(h2);
-        AL[OWED(2)] += raw(l2);
-        AH[OWED(3)] += raw(h3);
-        AL[OWED(3)] += raw(l3);
+      const double bnext = bp[0];                  // the last row reads the pad row
+      {
+        const double hi = __fma_rz(av[0], bj, C1);
+        const double lo = __fma_rz(av[0], bj, __dsub_rn(C12, hi));
+        AH[rr % L] += raw(hi);
+        AL[rr % L] += raw(lo);
       }
-      // ---- chain A, step 2
+      if (PAIR && inject) {
+        const uint64_t c = qp[0];                  // complement digit j of the previous pass's quotient
+        if (low_lane) AL[rr % L] += c;
+      }
+      // quotient digit: q = (column 0 mod 2^52) * n' mod 2^52 (the outstanding exponent constants have zero low bits)
+      const double v0 = u52_to_double(AL[rr % L] & MASK52);
       const double qh = __fma_rz(v0, np, C1);
-      if (rr > 0) {
-#pragma unroll
-        for (int i = 4; i < L; i += 2) {
-          const double ha = SCB_PROD_HI(nv[i], qprev), hb = (i + 1 < L) ? SCB_PROD_HI(nv[(i + 1) % L], qprev) : 0.0;
-          const double la = SCB_PROD_LO(nv[i], qprev, ha);
-          AH[OWED(i)] += raw(ha);
-          AL[OWED(i)] += raw(la);
-          if (i + 1 < L) {
-            const double lb = SCB_PROD_LO(nv[(i + 1) % L], qprev, hb);
-            AH[OWED(i + 1)] += raw(hb);
-            AL[OWED(i + 1)] += raw(lb);
-          }
-        }
-      }
-      // ---- chain A, step 3
-      const double qs = __dsub_rn(C1, qh);
-      {
-        // a_1 b_j, a_2 b_j
-        const double h1 = SCB_PROD_HI(av[1], b0), h2 = SCB_PROD_HI(av[2], b0);
-        const double l1 = SCB_PROD_LO(av[1], b0, h1), l2 = SCB_PROD_LO(av[2], b0, h2);
-        AH[COL(1)] += raw(h1);
-        AL[COL(1)] += raw(l1);
-        AH[COL(2)] += raw(h2);
-        AL[COL(2)] += raw(l2);
-      }
-      // ---- chain A, step 4: q = lo(v0 * n')
-      double q = __fma_rz(v0, np, qs);
-      {
-        // a_3 b_j, a_4 b_j, and a_0 b_{j+1} one row early (column 1 is column 0 of the next row)
-        const double h3 = SCB_PROD_HI(av[3], b0), h4 = SCB_PROD_HI(av[4], b0), hn = SCB_PROD_HI(av[0], b1);
-        const double l3 = SCB_PROD_LO(av[3], b0, h3), l4 = SCB_PROD_LO(av[4], b0, h4), ln = SCB_PROD_LO(av[0], b1, hn);
-        AH[COL(3)] += raw(h3);
-        AL[COL(3)] += raw(l3);
-        AH[COL(4)] += raw(h4);
-        AL[COL(4)] += raw(l4);
-        AH[COL(1)] += raw(hn);
-        AL[COL(1)] += raw(ln);
-      }
-      // ---- chain A, step 5: broadcast from the lane that owns column 0 of the number
+      double q = __fma_rz(v0, np, __dsub_rn(C1, qh));
+#ifndef SCB_EXP_NO_SHFL
       q = __shfl_sync(FULL, q, 0, TPI);
-      if (PAIR && inject && low_lane) AL[COL(1)] += cnext;
-#pragma unroll
-      for (int i = 5; i < L; i += 2) {
-        const double ha = SCB_PROD_HI(av[i], b0), hb = (i + 1 < L) ? SCB_PROD_HI(av[(i + 1) % L], b0) : 0.0;
-        const double la = SCB_PROD_LO(av[i], b0, ha);
-        AH[COL(i)] += raw(ha);
-        AL[COL(i)] += raw(la);
-        if (i + 1 < L) {
-          const double lb = SCB_PROD_LO(av[(i + 1) % L], b0, hb);
-          AH[COL(i + 1)] += raw(hb);
-          AL[COL(i + 1)] += raw(lb);
-        }
-      }
+#endif
+#ifdef SCB_EXP_NO_CHAIN
+      q = bnext;                                   /* experiment (tools/rowloop_microbench.cu): no serial quotient chain */
+#endif
       if (PAIR && save) {
-        if (low_lane) qout[0] = double_to_u52(q) ^ MASK52;
+        if (low_lane) qp[0] = double_to_u52(q) ^ MASK52;
       }
-      qout += GPW;
-      // ---- chain B: n_0 q, n_1 q complete columns 0 and 1
-      {
-        const double h0 = SCB_PROD_HI(nv[0], q), h1 = SCB_PROD_HI(nv[1], q);
-        const double l0 = SCB_PROD_LO(nv[0], q, h0), l1 = SCB_PROD_LO(nv[1], q, h1);
-        AH[COL(0)] += raw(h0);
-        AL[COL(0)] += raw(l0);
-        AH[COL(1)] += raw(h1);
-        AL[COL(1)] += raw(l1);
+      if (PAIR) qp += GPW;
+#pragma unroll
+      for (int i = 1; i < L; i++) {
+        const double hi = __fma_rz(av[i], bj, C1);
+        const double lo = __fma_rz(av[i], bj, __dsub_rn(C12, hi));
+#ifndef SCB_EXP_NO_IADD
+        AH[(i + rr) % L] += raw(hi);
+        AL[(i + rr) % L] += raw(lo);
+#else
+        AL[(i + rr) % L] ^= raw(hi) ^ raw(lo);     /* experiment: logic ops instead of the 64-bit adds */
+#endif
+      }
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        const double hi = __fma_rz(nv[i], q, C1);
+        const double lo = __fma_rz(nv[i], q, __dsub_rn(C12, hi));
+#ifndef SCB_EXP_NO_IADD
+        AH[(i + rr) % L] += raw(hi);
+        AL[(i + rr) % L] += raw(lo);
+#else
+        AL[(i + rr) % L] ^= raw(hi) ^ raw(lo);
+#endif
       }
       // column 0 is complete (all its exponent constants are cancelled): push its carry up, hand its low part down
-      const uint64_t t0 = AL[COL(0)];
-      AL[COL(1)] += AH[COL(0)] + (t0 >> 52);
+      const uint64_t t0 = AL[rr % L];
+      AL[(1 + rr) % L] += AH[rr % L] + (t0 >> 52);
       const uint64_t low = t0 & MASK52;             // 0 in lane 0 (Montgomery)
+#ifndef SCB_EXP_NO_SHFL
       const uint64_t in = __shfl_down_sync(FULL, low, 1, TPI);
-      AL[COL(0)] = (top ? 0ull : in) - 2ull * L * BITS_2P52;    // becomes logical column L-1 of the next row
-      AH[COL(0)] = 0ull - 2ull * L * BITS_2P104;
-      if (rr == L - 1) {
-        // last row of the block: pay n_i q, i >= 2, before the back-edge
-#pragma unroll
-        for (int i = 2; i < L; i += 2) {
-          const double ha = SCB_PROD_HI(nv[i], q), hb = (i + 1 < L) ? SCB_PROD_HI(nv[(i + 1) % L], q) : 0.0;
-          const double la = SCB_PROD_LO(nv[i], q, ha);
-          AH[COL(i)] += raw(ha);
-          AL[COL(i)] += raw(la);
-          if (i + 1 < L) {
-            const double lb = SCB_PROD_LO(nv[(i + 1) % L], q, hb);
-            AH[COL(i + 1)] += raw(hb);
-            AL[COL(i + 1)] += raw(lb);
-          }
-        }
-      }
-      qprev = q;
-      b0 = b1;
-      b1 = b2;
-#undef COL
-#undef OWED
+#else
+      const uint64_t in = low;
+#endif
+      AL[rr % L] = (top ? 0ull : in) - 2ull * L * BITS_2P52;    // becomes logical column L-1 of the next row
+      AH[rr % L] = 0ull - 2ull * L * BITS_2P104;
+      bj = bnext;
     }
   }
-  // after TPI*L rows the renaming is back to the identity.  The column at final position p lived only L-1-p rows: give
-  // back the exponent constants of the p+1 rows it did not see; position 0 also took the (zero) product a_0 b_K early.
+  // after TPI*L rows the renaming is back to the identity.  The column at final position p lived only L-1-p rows:
+  // give back the exponent constants of the p+1 rows it did not see.
 #pragma unroll
   for (int p = 0; p < L; p++) {
-    AL[p] += 2ull * (p + 1) * BITS_2P52 - (p == 0 ? BITS_2P52 : 0ull);
-    AH[p] += 2ull * (p + 1) * BITS_2P104 - (p == 0 ? BITS_2P104 : 0ull);
+    AL[p] += 2ull * (p + 1) * BITS_2P52;
+    AH[p] += 2ull * (p + 1) * BITS_2P104;
   }
   // fold the high accumulators one column up
   col[0] = AL[0];
@@ -302,17 +232,6 @@ __device__ __forceinline__ void mmd_rows(const double (&av)[L], const double (&n
   uint64_t col[L], hi_last;
   mmd_rows_core<L, TPI, false>(av, nv, np, sm_group, nullptr, 0, col, hi_last);
   resolve_carries<L, TPI>(col, hi_last, r);
-}
-
-// rows K and K+1 of a staging area must read as 0.0 (see mmd_rows_core); stage_digits52 never touches them
-template <int L, int TPI>
-__device__ __forceinline__ void zero_pad_rows52(double* sm_area) {
-  constexpr int GPW = Geo52<L, TPI>::GPW;
-  if ((threadIdx.x & 31) % TPI == 0) {
-    sm_area[Geo52<L, TPI>::K * GPW] = 0.0;
-    sm_area[(Geo52<L, TPI>::K + 1) * GPW] = 0.0;
-  }
-  __syncwarp();
 }
 
 // Stage this lane's L digits into the group's shared-memory operand area and make them visible.

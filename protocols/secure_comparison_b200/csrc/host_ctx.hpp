@@ -60,6 +60,7 @@ struct scb_ctx {
   // Paillier CRT form: device exponents [e1p, p, p-1, e1q, q, q-1] (kP words each) and their bit lengths
   bool have_paillier_crt = false, use_crt = true;
   bool use_f64 = true;                // large exponentiations on the FP64 engine (bn52.cuh) instead of the IMAD engine
+  bool use_small_batch = true;        // spread one number over twice the lanes when the batch cannot fill the GPU (L = 5 geometries)
   bool use_pair = true;               // exponentiations modulo a linked square n^2 in base-n pair form (half the digit products)
   bool fb_wide = true;                // build 16-bit-window fixed-base tables when memory allows
   uint32_t* crt_exp_dev = nullptr;

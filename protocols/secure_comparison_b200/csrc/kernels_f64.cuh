@@ -268,7 +268,6 @@ k_modexp52(const Modulus52Dev* __restrict__ m, const uint32_t* __restrict__ base
   using GI = GroupIndex52<L, TPI>;
   constexpr int K = Geo52<L, TPI>::K;
   double* sm_group = GI::warp_smem(smem52) + (threadIdx.x & 31) / TPI;
-  zero_pad_rows52<L, TPI>(sm_group);
   const size_t slot = GI::slot();
   double* X = scratch + slot * modexp52_scratch_doubles<L, TPI>(wbits);
   double* ACC = X + K;

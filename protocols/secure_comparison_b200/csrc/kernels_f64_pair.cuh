@@ -39,9 +39,9 @@ template <int L, int TPI>
 struct GeoPair {
   static constexpr int K = L * TPI;
   static constexpr int GPW = 32 / TPI;
-  static constexpr int S2_OFF = (K + 2) * GPW;           // second streamed-operand area (each: K digits + 2 zero rows)
-  static constexpr int Q_OFF = 2 * (K + 2) * GPW;        // complemented quotient digits of pass 1 (uint64; K + 1 zero row)
-  static constexpr int WARP_SMEM_WORDS64 = (3 * K + 5) * GPW;
+  static constexpr int S2_OFF = (K + 1) * GPW;           // second streamed-operand area (each: K digits + the prefetch pad row)
+  static constexpr int Q_OFF = 2 * (K + 1) * GPW;        // complemented quotient digits of pass 1 (uint64, K of them)
+  static constexpr int WARP_SMEM_WORDS64 = (3 * K + 2) * GPW;
 };
 
 // The row loop with the two hooks of the pair arithmetic: bn52.cuh, mmd_rows_core<L, TPI, true>.
@@ -455,10 +455,6 @@ k_modexp52p(const Modulus52Dev* __restrict__ m, const PairConsts52Dev* __restric
   using GP = GeoPair<L, TPI>;
   constexpr int K = Geo52<L, TPI>::K;
   double* sm_group = smem52 + (threadIdx.x >> 5) * GP::WARP_SMEM_WORDS64 + (threadIdx.x & 31) / TPI;
-  zero_pad_rows52<L, TPI>(sm_group);
-  zero_pad_rows52<L, TPI>(sm_group + GP::S2_OFF);
-  if ((threadIdx.x & 31) % TPI == 0) reinterpret_cast<uint64_t*>(sm_group + GP::Q_OFF)[K * GP::GPW] = 0ull;
-  __syncwarp();
   const size_t slot = GI::slot();
   double* XA = scratch + slot * modexp52p_scratch_doubles<L, TPI>(wbits);
   double* XB = XA + K;

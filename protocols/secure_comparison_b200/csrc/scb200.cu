@@ -793,30 +793,40 @@ int scb::modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, con
                     const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   const scb_ctx::Mod& md = ctx->mod[slot];
   if (kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp: output narrower than the modulus");
+  // Small batches: when the batch cannot fill half of the resident groups of the usual geometry (L = 10 digits per lane), the
+  // same number is spread over twice as many lanes (L = 5): half the latency per exponentiation, twice the SMs busy.
+  auto small_batch = [&](int tpi_big) -> bool {
+    const size_t resident = static_cast<size_t>(ctx->num_sms) * 3 * WARPS_PER_BLOCK * (32 / tpi_big);
+    return ctx->use_small_batch && B * 2 <= resident;
+  };
   // square modulus linked to its root: base-root pair form on the FP64 engine (half the digit products)
   if (ctx->use_f64 && ctx->use_pair && md.root_slot >= 0 && md.pair52 && mul_in == nullptr && exp_bits >= 64) {
     const scb_ctx::Mod& rt = ctx->mod[md.root_slot];
+#define PAIRCALL(L, TPI) launch_modexp52p<L, TPI>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B)
     switch (rt.K52) {
-      case 20: return launch_modexp52p<10, 2>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
-      case 30: return launch_modexp52p<15, 2>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
-      case 40: return launch_modexp52p<10, 4>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
-      case 60: return launch_modexp52p<15, 4>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
-      case 80: return launch_modexp52p<10, 8>(ctx, md, rt, base, kbase, exp, exp_words, estride, exp_bits, out, kout, B);
+      case 20: return small_batch(2) ? PAIRCALL(5, 4) : PAIRCALL(10, 2);
+      case 30: return PAIRCALL(15, 2);
+      case 40: return small_batch(4) ? PAIRCALL(5, 8) : PAIRCALL(10, 4);
+      case 60: return PAIRCALL(15, 4);
+      case 80: return small_batch(8) ? PAIRCALL(5, 16) : PAIRCALL(10, 8);
       default: break;
     }
+#undef PAIRCALL
   }
   // FP64 engine for real exponentiations (it has no advantage for the few-bit exponents of the DGK blinding)
   if (ctx->use_f64 && md.K52 > 0 && exp_bits >= 64 && 32 * kbase <= 104 * md.K52) {
+#define F64CALL(L, TPI) launch_modexp52<L, TPI>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B)
     switch (md.K52) {
-      case 20: return launch_modexp52<10, 2>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 30: return launch_modexp52<15, 2>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 40: return launch_modexp52<10, 4>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 60: return launch_modexp52<15, 4>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 120: return launch_modexp52<15, 8>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 80: return launch_modexp52<10, 8>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
-      case 160: return launch_modexp52<10, 16>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B);
+      case 20: return small_batch(2) ? F64CALL(5, 4) : F64CALL(10, 2);
+      case 30: return F64CALL(15, 2);
+      case 40: return small_batch(4) ? F64CALL(5, 8) : F64CALL(10, 4);
+      case 60: return F64CALL(15, 4);
+      case 120: return F64CALL(15, 8);
+      case 80: return small_batch(8) ? F64CALL(5, 16) : F64CALL(10, 8);
+      case 160: return F64CALL(10, 16);
       default: break;
     }
+#undef F64CALL
   }
   if (32 * kbase > 2 * W * md.K) return fail(ctx, SCB_EINVAL, "modexp: base wider than twice the modulus");
 #define CALL(L, TPI) launch_modexp<L, TPI>(ctx, md, base, kbase, exp, exp_words, estride, exp_bits, mul_in, out, kout, B)

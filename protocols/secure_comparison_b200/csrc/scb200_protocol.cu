@@ -374,6 +374,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
     case SCB_OPT_MODEXP_FP64: ctx->use_f64 = value != 0; return SCB_OK;
     case SCB_OPT_SLIDING_WINDOWS: ctx->use_sliding = value != 0; return SCB_OK;
     case SCB_OPT_SQUARE_MODULUS: ctx->use_pair = value != 0; return SCB_OK;
+    case SCB_OPT_SMALL_BATCH: ctx->use_small_batch = value != 0; return SCB_OK;
     case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }

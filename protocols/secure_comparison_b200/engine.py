@@ -164,6 +164,10 @@ class Engine:
         """Pair-form exponentiation for linked square moduli (default) or n^2 as an ordinary modulus; bit-identical results."""
         self._check(self.lib.scb_set_option(self.ctx, nat.OPT_SQUARE_MODULUS, int(bool(enabled))))
 
+    def set_small_batch(self, enabled: bool) -> None:
+        """Small batches on twice the lanes per number (default) or always the 10-digits-per-lane geometry; bit-identical results."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_SMALL_BATCH, int(bool(enabled))))
+
     def modulus(self, slot: int) -> int:
         return self._moduli[slot][0]
 
