@@ -7,11 +7,11 @@
 // <= 2^29, and only final outputs are reduced to the canonical residue in [0, n) (what GMP / CPython
 // return in the reference).
 //
-// Why 29-bit digits.  On B200 the carry-less IMAD.WIDE.U32 (32x32+64 -> 64) issues at the full
-// 64 lanes/clk/SM, while the carry-chained form IMAD.WIDE.U32.X (what mad.lo.cc/madc.hi.cc compile
-// to, and what a radix-2^32 CIOS needs) only reaches ~27.5/clk/SM (measured: profiles/
-// r01_imad_microbench.jsonl).  With 29-bit digits a product is < 2^58, and a 64-bit column
-// accumulator can absorb the 2*L <= 62 products it sees while it belongs to one lane, so the whole
+// Why 29-bit digits.  On B200 the accumulating IMAD.WIDE.U32 Rd, Ra, Rb, Rc (32x32+64 -> 64) issues on the fmaheavy
+// pipe only, 32 lanes/clk/SM nominal (measured 29.6: 8.6 TMAC/s, profiles/r01_imad_microbench2.jsonl and
+// scb_measure_peak); the carry-chained form IMAD.WIDE.U32.X (what mad.lo.cc/madc.hi.cc compile to, and what a
+// radix-2^32 CIOS needs) reaches 27.5/clk/SM, IMAD.HI + IMAD.LO pairs 18.  With 29-bit digits a product is < 2^58, and a
+// 64-bit column accumulator can absorb the 2*L <= 62 products it sees while it belongs to one lane, so the whole
 // inner loop is carry-less IMAD.WIDE.U32 with one 64-bit shift/add per row.
 //
 // One Montgomery product r = a*b*R^-1 mod n (CIOS by rows, one digit b_j per row):

@@ -793,11 +793,12 @@ int scb::modexp_any(scb_ctx* ctx, int slot, const uint32_t* base, int kbase, con
                     const uint32_t* mul_in, uint32_t* out, int kout, size_t B) {
   const scb_ctx::Mod& md = ctx->mod[slot];
   if (kout < md.k32) return fail(ctx, SCB_EINVAL, "modexp: output narrower than the modulus");
-  // Small batches: when the batch cannot fill half of the resident groups of the usual geometry (L = 10 digits per lane), the
-  // same number is spread over twice as many lanes (L = 5): half the latency per exponentiation, twice the SMs busy.
+  // Small batches: when the batch fills less than a quarter of the resident groups of the usual geometry (L = 10 digits per
+  // lane) the launch is bound by the latency of ONE exponentiation, and the same number is spread over twice as many lanes
+  // (L = 5): measured 1.42x at B = 1,024 and 2,048 (2048-bit), break-even near B = 4,096 (profiles/r02c_small_batch_*.jsonl).
   auto small_batch = [&](int tpi_big) -> bool {
     const size_t resident = static_cast<size_t>(ctx->num_sms) * 3 * WARPS_PER_BLOCK * (32 / tpi_big);
-    return ctx->use_small_batch && B * 2 <= resident;
+    return ctx->use_small_batch && B * 4 <= resident;
   };
   // square modulus linked to its root: base-root pair form on the FP64 engine (half the digit products)
   if (ctx->use_f64 && ctx->use_pair && md.root_slot >= 0 && md.pair52 && mul_in == nullptr && exp_bits >= 64) {

@@ -30,15 +30,19 @@ SIZES = [(64, 64, 40), (128, 160, 70), (1024, 160, 300), (1024, 1024, 200), (153
          (3072, 400, 100), (4096, 2048, 70), (6144, 64, 40), (8192, 96, 40), (1000, 70, 64), (2040, 333, 64), (4090, 100, 33)]
 
 
-@pytest.mark.parametrize("fp64", [True, False], ids=["fp64", "imad"])
+@pytest.mark.parametrize("engine", ["fp64", "fp64-wide-lanes", "imad"])
 @pytest.mark.parametrize("bits,ebits,B", SIZES)
-def test_modexp_matches_pow(eng, bits, ebits, B, fp64):
-    """Both multiplier engines (FP64-pipe 52-bit digits, IMAD 29-bit digits) against Python's pow."""
-    eng.set_modexp_fp64(fp64)
+def test_modexp_matches_pow(eng, bits, ebits, B, engine):
+    """Both multiplier engines (FP64-pipe 52-bit digits, IMAD 29-bit digits) against Python's pow.  These batches are small, so by
+    default the FP64 engine spreads every number over twice the lanes (5 digits per lane); "fp64" switches that off and
+    runs the throughput geometry (10 digits per lane) that full-size batches use."""
+    eng.set_modexp_fp64(engine != "imad")
+    eng.set_small_batch(engine == "fp64-wide-lanes")
     try:
         _modexp_matches_pow(eng, bits, ebits, B)
     finally:
         eng.set_modexp_fp64(True)
+        eng.set_small_batch(True)
 
 
 def _modexp_matches_pow(eng, bits, ebits, B):
@@ -66,10 +70,12 @@ SQUARE_SIZES = [(512, 512, 40), (1024, 1024, 150), (1036, 200, 64), (1536, 160, 
                 (4096, 300, 40), (100, 64, 33)]
 
 
+@pytest.mark.parametrize("wide_lanes", [False, True], ids=["10-digits-per-lane", "5-digits-per-lane"])
 @pytest.mark.parametrize("bits,ebits,B", SQUARE_SIZES)
-def test_modexp_square_modulus_pair_form(eng, bits, ebits, B):
+def test_modexp_square_modulus_pair_form(eng, bits, ebits, B, wide_lanes):
     """Exponentiation modulo a linked square n^2 (base-n pair arithmetic, tests/pairmul_model.py) against Python's pow and
     against the plain engine on the same slot; bases wider than n (reduced on load), per-element and shared exponents."""
+    eng.set_small_batch(wide_lanes)
     rng = random.Random(bits * 13 + ebits)
     n = rand_modulus(rng, bits)
     root, sq = nat.MOD_USER0 + 1, nat.MOD_USER0 + 2
@@ -105,6 +111,7 @@ def test_modexp_square_modulus_pair_form(eng, bits, ebits, B):
     eng.load_modulus(root, n)                        # reloading the root drops the link (results stay correct)
     out = eng.modexp(sq, ints_to_limbs(bases[:8], k2), ints_to_limbs([e_shared], ew)[0], ebits)
     assert limbs_to_ints(out) == want_shared[:8]
+    eng.set_small_batch(True)
 
 
 @pytest.mark.parametrize("bits", [64, 1024, 2048, 3072, 4096, 8192])

@@ -165,6 +165,7 @@ def test_ciphertexts_match_oracle_at_scale(key_spec, B):
     paillier, dgk = make_schemes(*key_spec)
     reset_engines()
     eng = get_engine(paillier, dgk, l)
+    eng.set_small_batch(False)       # the throughput geometry of full-size batches (these batches alone would get 5 digits per lane)
     rng = random.Random(65536)
     pairs = draw_inputs(rng, B, l)
     N = paillier.public_key.n

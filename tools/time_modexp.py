@@ -34,8 +34,12 @@ def main():
     ap.add_argument("--batches", default="1024,4096,16384,65536")
     ap.add_argument("--engines", default="fp64,imad")
     ap.add_argument("--ebits", default="", help="exponent length (default: the modulus length); e.g. 160 with --bits 1024 = DGK is-zero")
+    ap.add_argument("--no-wide-lanes", action="store_true", help="keep 10 digits per lane for small batches too (SCB_OPT_SMALL_BATCH = 0)")
+    ap.add_argument("--max-seconds", type=float, default=0.0, help="skip batch sizes whose predicted time (from the previous size) exceeds this")
     args = ap.parse_args()
     eng = Engine(0)
+    if args.no_wide_lanes:
+        eng.set_small_batch(False)
     stream = torch.cuda.ExternalStream(eng.stream_ptr)
     rng = random.Random(1)
     for bits in [int(v) for v in args.bits.split(",")]:
@@ -45,7 +49,10 @@ def main():
         ew = (ebits + 31) // 32
         for engine in args.engines.split(","):
             eng.set_modexp_fp64(engine == "fp64")
+            last = None
             for B in [int(v) for v in args.batches.split(",")]:
+                if args.max_seconds and last and last[1] * B / last[0] > args.max_seconds * 1e3:
+                    continue
                 base = np.random.default_rng(0).integers(0, 1 << 32, size=(B, k), dtype=np.uint64).astype(np.uint32)
                 base[:, -1] &= 0x7FFFFFFF
                 exp = np.random.default_rng(1).integers(0, 1 << 32, size=(B, ew), dtype=np.uint64).astype(np.uint32)
@@ -67,8 +74,9 @@ def main():
                 got = limbs_to_ints(d_out[:4].cpu().numpy().view(np.uint32))
                 want = [pow(int.from_bytes(base[i].tobytes(), "little"), int.from_bytes(exp[i].tobytes(), "little"), n) for i in range(4)]
                 rate = B / (ms * 1e-3)
+                last = (B, ms)
                 print(json.dumps({"bits": bits, "exponent_bits": ebits, "engine": engine, "B": B, "ms": round(ms, 3), "modexp_per_s": round(rate, 1),
-                                  "parity_sample": got == want,
+                                  "parity_sample": got == want, "wide_lanes_for_small_batches": not args.no_wide_lanes,
                                   "frac_of_int_roofline": round(rate * algorithmic_mac(bits, ebits) / PEAK_MAC, 4)}), flush=True)
 
 
