@@ -393,7 +393,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL may print its version banner on stdout when the communicator comes up; stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         torch.cuda.synchronize()
@@ -677,6 +688,18 @@ def run_ours(args):
                                  "matches_device_path": bool(np.array_equal(res2, dp.res.cpu().numpy().view(np.uint32))),
                                  "api": "LocalPipeline.compare (host-pointer C-ABI calls, 2 contexts x 2 chunks, host-supplied nonces)"}
         pipe.close()
+        # the one-process multi-GPU form of the same pipeline (LocalPipeline(devices=[...]): one context and worker thread per GPU,
+        # batch sharded by index): exercised on two GPUs whenever this job has them (rank 0; the other ranks idle at the barrier)
+        if world >= 2:
+            if rank == 0:
+                nb = min(B, 4096)
+                sub = {k: v[:nb] for k, v in h.items()}
+                pipe2 = LocalPipeline(paillier, dgk, l, n_contexts=1, devices=[0, 1])
+                out2 = pipe2.compare(sub)
+                e2e["local_pipeline_two_gpus"] = {"devices": [0, 1], "comparisons": int(nb),
+                                                  "matches_device_path": bool(np.array_equal(out2, dp.res[:nb].cpu().numpy().view(np.uint32)))}
+                pipe2.close()
+            barrier()
         del h
 
     # ---- BASELINE configs[2] and configs[3]: shard legs (N > 1, or on request)

@@ -121,7 +121,9 @@ constexpr int PASS_INJECT = 2;   // add the stored complement (+1) into the low 
 // instruction mix, not latency -- 211-215 cycles per warp-row and scheduler whether 1, 2, 3 or 4 blocks are resident per SM.
 // Breaking the serial quotient chain on purpose buys 9 %, dropping the shuffles 4 %, replacing the 64-bit adds nothing; a
 // software-pipelined variant of this loop (a_0 b_{j+1} one row early, products of the previous row's quotient digit inside
-// the next chain, accumulation delayed by one product pair) measured the same 215 cycles, so the plain form stays.
+// the next chain, accumulation delayed by one product pair) measured the same 215 cycles, and a fused sweep that runs both
+// passes of a pair squaring at once (two accumulator sets, 244 registers, a 40 KB unrolled body) measured 243 cycles per
+// row-equivalent against 228 for two separate passes (profiles/r02_rowloop_microbench_dual.jsonl): the plain form stays.
 template <int L, int TPI, bool PAIR>
 __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const double (&nv)[L], const double np, const double* __restrict__ sm_stream,
                                               uint64_t* __restrict__ sm_q, const int flags, uint64_t (&col)[L], uint64_t& hi_last) {
