@@ -445,8 +445,15 @@ __device__ __forceinline__ void group_modexp52_pair(const Modulus52Dev* __restri
 }
 
 // out[i] = base[i]^exp[i] mod n^2 (n = the root modulus `m`); base: kbase words (any value, reduced on load)
+// Two blocks per SM (255 registers), not three: the pair loop keeps two more L-digit values alive than k_modexp52, and at the
+// 168-register cap of three blocks ptxas not only spilled them but, starved of temporaries, scheduled the row loop with its
+// FP64 results consumed 1-6 instructions after they were issued (tools/sass_deps.py); the row loop itself does not care about
+// occupancy (profiles/r02_rowloop_microbench.jsonl).  Measured at B = 65,536: 371 -> 340 ms (10x4), 420 -> 388 ms (10x2).
+#ifndef SCB_PAIR_BLOCKS_PER_SM
+#define SCB_PAIR_BLOCKS_PER_SM 2
+#endif
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 3 : 2))
+__global__ void __launch_bounds__(BLOCK_THREADS, SCB_PAIR_BLOCKS_PER_SM)
 k_modexp52p(const Modulus52Dev* __restrict__ m, const PairConsts52Dev* __restrict__ pc, const uint32_t* __restrict__ base, int kbase,
             const uint32_t* __restrict__ exp, int ewords, size_t exp_stride, int ebits, int wbits, double* scratch, uint32_t* __restrict__ out, int kout,
             size_t B, unsigned long long* queue, const uint16_t* __restrict__ prog, int nprog, int pw) {
