@@ -374,12 +374,19 @@ __device__ __forceinline__ void group_modexp52_pair(const Modulus52Dev* __restri
       }
       if (op_square) stage_digits52<L, TPI>(s1, ra);
     } else if (pass == 1 && op_square) {
-      // stream 2b (normalised digits) for the cross term of the squaring
-      uint64_t c2[L];
+      // stream 2b for the cross term of the squaring: the digits of b are normalised, so doubling is a one-bit shift across the
+      // digits (the bit leaving a lane's top digit enters the next lane; 2b < 8n < R, nothing leaves the number)
+      uint64_t d[L];
       double b2[L];
 #pragma unroll
-      for (int i = 0; i < L; i++) c2[i] = 2ull * double_to_u52(rb[i]);
-      resolve_carries<L, TPI>(c2, 0ull, b2);
+      for (int i = 0; i < L; i++) d[i] = double_to_u52(rb[i]);
+      uint32_t carry_in = __shfl_up_sync(FULL, static_cast<uint32_t>(d[L - 1] >> 51), 1, TPI);
+      if (t == 0) carry_in = 0u;
+#pragma unroll
+      for (int i = L - 1; i >= 1; i--) d[i] = ((d[i] << 1) & MASK52) | (d[i - 1] >> 51);
+      d[0] = ((d[0] << 1) & MASK52) | carry_in;
+#pragma unroll
+      for (int i = 0; i < L; i++) b2[i] = u52_to_double(d[i]);
       stage_digits52<L, TPI>(s1, b2);
     }
     uint64_t col[L], hi;
