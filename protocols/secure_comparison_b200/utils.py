@@ -15,23 +15,15 @@ from .limbs import int_to_limbs, ints_to_limbs
 
 
 def to_bits(integer: int, bit_length: int) -> List[int]:
-    """Reference ``utils.py:6-21``."""
+    """``bit_length`` bits of ``integer``, least significant first (contract of reference ``utils.py:6-21``, including its
+    assertion that the integer fits)."""
     assert integer < (1 << bit_length)
-    bits = [0 for _ in range(bit_length)]
-    for bit_index in range(bit_length):
-        bits[bit_index] = integer & 1
-        integer >>= 1
-    return bits
+    return [(integer >> position) & 1 for position in range(bit_length)]
 
 
 def from_bits(bits: Sequence[int]) -> int:
-    """Reference ``utils.py:24-38``."""
-    base, integer = 1, 0
-    for bit in bits:
-        if bit == 1:
-            integer += base
-        base *= 2
-    return integer
+    """Inverse of ``to_bits`` (reference ``utils.py:24-38``): bits are least significant first; only entries equal to 1 count."""
+    return sum(1 << position for position, bit in enumerate(bits) if bit == 1)
 
 
 def to_bits_batch(values: np.ndarray, bit_length: int) -> np.ndarray:
