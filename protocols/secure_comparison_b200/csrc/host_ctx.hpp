@@ -12,6 +12,7 @@ struct ModulusDev;
 struct Modulus52Dev;
 struct PairConsts52Dev;
 struct KeysDev;
+struct Keys52Dev;
 }  // namespace scb
 
 struct scb_ctx {
@@ -24,6 +25,7 @@ struct scb_ctx {
     int K = 0, k32 = 0, bits = 0, K52 = 0;
     bool loaded = false;
     std::vector<uint32_t> words;
+    std::vector<uint32_t> r52_words;      // R mod n of the FP64 engine (R = 2^(52 K52)) as k32 words: x * r52 mod n = Montgomery form of x
     // this modulus is the SQUARE of the modulus in slot `root_slot` (scb_modulus_link_square): exponentiations run in
     // base-root pair form on the FP64 engine (kernels_f64_pair.cuh); pair52 = their constants
     int root_slot = -1;
@@ -32,6 +34,9 @@ struct scb_ctx {
   struct FixedBase {
     uint32_t* table = nullptr;   // [nwin][256][K] Montgomery digits (8-bit windows)
     uint32_t* table16 = nullptr; // [nwin16][65536][K] (16-bit windows; optional, built from `table`)
+    double* table52 = nullptr;   // the same two tables in the FP64 engine's digits ([..][K52] doubles), for the DGK phases on that engine
+    double* table16_52 = nullptr;
+    const double* use_table52() const { return table16_52 ? table16_52 : table52; }
     int nwin = 0, nwin16 = 0, slot = -1, exp_bits = 0;
     // what the exponentiation kernels use
     const uint32_t* use_table() const { return table16 ? table16 : table; }
@@ -51,6 +56,8 @@ struct scb_ctx {
   size_t scratch_bytes[NSCRATCH] = {0};
   std::map<const void*, int> occupancy_cache;
   scb::KeysDev* keys_dev = nullptr;   // protocol-level key material (kernels_protocol.cuh)
+  scb::Keys52Dev* keys52_dev = nullptr;   // DGK constants in the FP64 engine's Montgomery form (kernels_dgk52.cuh); null = not available
+  bool use_dgk52 = true;              // DGK-side phases on the FP64 engine when its tables exist (follows use_f64)
   std::vector<uint8_t> keys_host;     // host mirror of KeysDev
   bool have_paillier_pub = false, have_paillier_priv = false, have_dgk_pub = false, have_dgk_priv = false;
   std::vector<uint32_t> paillier_lambda, paillier_mu, dgk_vp;

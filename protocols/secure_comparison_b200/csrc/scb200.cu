@@ -15,6 +15,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_f64.cuh"
 #include "kernels_f64_pair.cuh"
+#include "kernels_fb52.cuh"
 
 using namespace scb;
 
@@ -273,10 +274,13 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   for (auto& t : ctx->fb) {
     if (t.table) cudaFree(t.table);
     if (t.table16) cudaFree(t.table16);
+    if (t.table52) cudaFree(t.table52);
+    if (t.table16_52) cudaFree(t.table16_52);
   }
   for (int i = 0; i < scb_ctx::NSCRATCH; i++)
     if (ctx->scratch_ptr[i]) cudaFree(ctx->scratch_ptr[i]);
   if (ctx->keys_dev) cudaFree(ctx->keys_dev);
+  if (ctx->keys52_dev) cudaFree(ctx->keys52_dev);
   if (ctx->secret_dev) cudaFree(ctx->secret_dev);
   if (ctx->vp_dev) cudaFree(ctx->vp_dev);
   if (ctx->crt_exp_dev) cudaFree(ctx->crt_exp_dev);
@@ -428,6 +432,7 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
     for (int t = 0; t < 3; t++) {
       for (; ee < targets52[t]; ee++) words_dbl_mod(y, nw);
       to52(y, dst52[t]);
+      if (t == 0) md.r52_words.assign(y.begin(), y.begin() + k32);
     }
     if (!md.dev52) {
       cudaError_t ce2 = cudaMalloc(&md.dev52, sizeof(Modulus52Dev));
@@ -438,6 +443,7 @@ extern "C" int scb_modulus_load(scb_ctx* ctx, int slot, const uint32_t* n, int k
     if (ce2 != cudaSuccess) return cuda_fail(ctx, ce2, "upload modulus52");
   } else {
     md.K52 = 0;
+    md.r52_words.clear();
   }
   return SCB_OK;
 }
@@ -608,6 +614,35 @@ int launch_modexp52(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base, 
   return ctx->launched(label);
 }
 
+// fixed-base tables in the FP64 engine's digits (kernels_fb52.cuh)
+template <int L, int TPI>
+int launch_fb52_build(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* base_dev, double* table, int nwin) {
+  using G = Geo52<L, TPI>;
+  k52_fb_bases<L, TPI><<<1, 32, sizeof(double) * G::WARP_SMEM_DOUBLES, ctx->stream>>>(md.dev52, base_dev, md.k32, table, nwin);
+  int rc = ctx->launched("k52_fb_bases");
+  if (rc) return rc;
+  const size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
+  k52_fb_fill<L, TPI><<<(nwin + gpb - 1) / gpb, BLOCK_THREADS, smem, ctx->stream>>>(md.dev52, table, nwin, table + static_cast<size_t>(nwin) * 256 * G::K);
+  return ctx->launched("k52_fb_fill");
+}
+
+template <int L, int TPI>
+int launch_fb52_16_build(scb_ctx* ctx, const scb_ctx::Mod& md, const double* table8, double* table16, int nwin16) {
+  using G = Geo52<L, TPI>;
+  const size_t smem = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  const int gpb = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
+  const size_t M = static_cast<size_t>(nwin16) << 16;
+  int grid = ctx->grid_for(reinterpret_cast<const void*>(&k52_fb16_fill<L, TPI>), smem, M, gpb);
+  void* dump = nullptr;
+  int rc = ctx->scratch(0, static_cast<size_t>(grid) * gpb * G::K * sizeof(double), &dump);
+  if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  k52_fb16_fill<L, TPI><<<grid, BLOCK_THREADS, smem, ctx->stream>>>(md.dev52, table8, table16, M, static_cast<double*>(dump), queue);
+  return ctx->launched("k52_fb16_fill");
+}
+
 // exponentiation modulo the square of `rt` (pair form, kernels_f64_pair.cuh)
 template <int L, int TPI>
 int launch_modexp52p(scb_ctx* ctx, const scb_ctx::Mod& sq, const scb_ctx::Mod& rt, const uint32_t* base, int kbase, const uint32_t* exp, int ewords,
@@ -704,6 +739,18 @@ int launch_fixed_base(scb_ctx* ctx, const scb_ctx::Mod& md, const scb_ctx::Fixed
     case 216: return CALL(27, 8);                                                 \
     case 288: return CALL(18, 16);                                                \
     default: return fail(ctx, SCB_EINVAL, "unsupported digit count %d", K);       \
+  }
+
+#define SCB_DISPATCH_K52(K52, CALL)                                              \
+  switch (K52) {                                                                  \
+    case 20: return CALL(10, 2);                                                  \
+    case 30: return CALL(15, 2);                                                  \
+    case 40: return CALL(10, 4);                                                  \
+    case 60: return CALL(15, 4);                                                  \
+    case 80: return CALL(10, 8);                                                  \
+    case 120: return CALL(15, 8);                                                 \
+    case 160: return CALL(10, 16);                                                \
+    default: return fail(ctx, SCB_EINVAL, "unsupported FP64 digit count %d", K52); \
   }
 
 int scb_ctx::grid_for(const void* kernel, size_t smem, size_t B, int groups_per_block) {
@@ -926,6 +973,14 @@ extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint
     cudaFree(fb.table16);
     fb.table16 = nullptr;
   }
+  if (fb.table52) {
+    cudaFree(fb.table52);
+    fb.table52 = nullptr;
+  }
+  if (fb.table16_52) {
+    cudaFree(fb.table16_52);
+    fb.table16_52 = nullptr;
+  }
   cudaError_t e = cudaMalloc(&fb.table, bytes);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(fixed-base table)");
   void* bdev = nullptr;
@@ -958,6 +1013,35 @@ extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint
 #undef CALL
       rc = run16();
       if (rc) return rc;
+    }
+  }
+  // the same tables in the FP64 engine's digits, for the DGK phases on that engine (kernels_dgk52.cuh)
+  if (ctx->use_f64 && md.K52 > 0 && md.dev52) {
+    const size_t bytes52 = (static_cast<size_t>(nwin) * 256 + 256) * md.K52 * sizeof(double);
+    e = cudaMalloc(&fb.table52, bytes52);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      fb.table52 = nullptr;
+    } else {
+      double* t52 = fb.table52;
+#define CALL(L, TPI) launch_fb52_build<L, TPI>(ctx, md, bd, t52, nwin)
+      auto run52 = [&]() -> int { SCB_DISPATCH_K52(md.K52, CALL) };
+#undef CALL
+      if ((rc = run52())) return rc;
+      const size_t bytes16_52 = (static_cast<size_t>(nwin16) << 16) * md.K52 * sizeof(double);
+      if (fb.table16 && bytes16_52 <= (static_cast<size_t>(8) << 30)) {
+        e = cudaMalloc(&fb.table16_52, bytes16_52);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          fb.table16_52 = nullptr;
+        } else {
+          double* t16 = fb.table16_52;
+#define CALL(L, TPI) launch_fb52_16_build<L, TPI>(ctx, md, t52, t16, nwin16)
+          auto run52b = [&]() -> int { SCB_DISPATCH_K52(md.K52, CALL) };
+#undef CALL
+          if ((rc = run52b())) return rc;
+        }
+      }
     }
   }
   rc = scb_sync(ctx);

@@ -8,6 +8,7 @@
 
 #include "host_ctx.hpp"
 #include "kernels_protocol.cuh"
+#include "kernels_dgk52.cuh"
 
 using namespace scb;
 
@@ -340,7 +341,46 @@ extern "C" int scb_dgk_set_public(scb_ctx* ctx, const uint32_t* n, const uint32_
   ctx->dgk_rand_bits = rand_bits;
   ctx->have_dgk_pub = true;
   ctx->have_dgk_priv = false;
-  return upload_keys(ctx);
+  if ((rc = upload_keys(ctx))) return rc;
+  // the same constants in the FP64 engine's Montgomery form (x * R52 mod n), derived with the library's own batched product
+  if (ctx->keys52_dev) {
+    cudaFree(ctx->keys52_dev);
+    ctx->keys52_dev = nullptr;
+  }
+  if (md.K52 > 0 && 2 * md.K52 <= 2 * MAXK52 && static_cast<int>(md.r52_words.size()) == kn) {
+    const int K52 = md.K52;
+    // canonical values: g, g_neg, g*g, g_neg*g
+    std::vector<uint32_t> vals(4 * kn), a2(2 * kn), b2(2 * kn), r52x4(4 * kn), mont(4 * kn);
+    memcpy(vals.data(), words.data(), sizeof(uint32_t) * 2 * kn);                  // g, g_neg
+    memcpy(a2.data(), words.data(), sizeof(uint32_t) * 2 * kn);                    // (g, g_neg) * (g, g)
+    memcpy(b2.data(), g, sizeof(uint32_t) * kn);
+    memcpy(b2.data() + kn, g, sizeof(uint32_t) * kn);
+    if ((rc = scb_modmul(ctx, SCB_MOD_DGK_N, a2.data(), b2.data(), vals.data() + 2 * kn, 2))) return rc;
+    for (int i = 0; i < 4; i++) memcpy(r52x4.data() + static_cast<size_t>(i) * kn, md.r52_words.data(), sizeof(uint32_t) * kn);
+    if ((rc = scb_modmul(ctx, SCB_MOD_DGK_N, vals.data(), r52x4.data(), mont.data(), 4))) return rc;
+    std::vector<uint8_t> buf(sizeof(Keys52Dev), 0);
+    Keys52Dev* h52 = reinterpret_cast<Keys52Dev*>(buf.data());
+    auto to52 = [&](const uint32_t* x, double* digits) {
+      for (int d = 0; d < K52; d++) {
+        const int bit = d * 52, w = bit >> 5, sh = bit & 31;
+        auto word = [&](int i) -> uint64_t { return i < kn ? x[i] : 0u; };
+        uint64_t v = (word(w) | (word(w + 1) << 32)) >> sh;
+        if (sh) v |= word(w + 2) << (64 - sh);
+        digits[d] = static_cast<double>(v & ((1ull << 52) - 1ull));
+      }
+    };
+    to52(mont.data(), h52->g_m);
+    to52(mont.data(), h52->c_sa[0][0]);                                  // enc(+1) * enc(0) = g
+    to52(mont.data() + static_cast<size_t>(2) * kn, h52->c_sa[0][1]);    // g * g
+    to52(mont.data() + static_cast<size_t>(1) * kn, h52->c_sa[1][0]);    // g_neg
+    to52(mont.data() + static_cast<size_t>(3) * kn, h52->c_sa[1][1]);    // g_neg * g
+    cudaError_t ce = cudaMalloc(&ctx->keys52_dev, sizeof(Keys52Dev));
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaMalloc(keys52)");
+    ce = cudaMemcpyAsync(ctx->keys52_dev, h52, sizeof(Keys52Dev), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "upload keys52");
+  }
+  return SCB_OK;
 }
 
 extern "C" int scb_dgk_set_private(scb_ctx* ctx, const uint32_t* p, int kp, const uint32_t* v_p, int vp_words, int vp_bits) {
@@ -690,6 +730,127 @@ int phase_step4(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const u
   return SCB_OK;
 }
 
+// ---- the same two phases on the FP64 engine (kernels_dgk52.cuh); L29 / TPI29 = the IMAD geometry of the same modulus (batched inverse)
+#define SCB_DISPATCH_K52(K52, CALL)                                               \
+  switch (K52) {                                                                  \
+    case 20: return CALL(10, 2);                                                  \
+    case 30: return CALL(15, 2);                                                  \
+    case 40: return CALL(10, 4);                                                  \
+    case 60: return CALL(15, 4);                                                  \
+    case 80: return CALL(10, 8);                                                  \
+    case 120: return CALL(15, 8);                                                 \
+    case 160: return CALL(10, 16);                                                \
+    default: return fail(ctx, SCB_EINVAL, "unsupported FP64 digit count %d", K52); \
+  }
+
+template <int L, int TPI>
+struct Cfg52 {
+  using G = Geo52<L, TPI>;
+  static constexpr size_t SMEM = sizeof(double) * G::WARP_SMEM_DOUBLES * WARPS_PER_BLOCK;
+  static constexpr int GPB = GroupIndex52<L, TPI>::GROUPS_PER_BLOCK;
+  static constexpr int K = G::K;
+};
+
+bool dgk52_ready(scb_ctx* ctx) {
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_N];
+  return ctx->use_f64 && ctx->use_dgk52 && md.K52 > 0 && md.dev52 && ctx->keys52_dev && ctx->fb[0].loaded && ctx->fb[0].table52;
+}
+
+template <int L, int TPI>
+int phase_dgk_encrypt_bits52(scb_ctx* ctx, const uint64_t* beta, const uint8_t* dflag, int l, const uint32_t* rho, int ew, uint32_t* out, size_t B) {
+  using C = Cfg52<L, TPI>;
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_N];
+  const scb_ctx::FixedBase& fb = ctx->fb[0];
+  const size_t M = B * (l + 1);
+  const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k52_dgk_encrypt_bits<L, TPI>), C::SMEM, M, C::GPB);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(SC_GROUP, sizeof(double) * static_cast<size_t>(grid) * C::GPB * 2 * C::K, &scratch);
+  if (rc) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  const bool wide = fb.table16_52 != nullptr;
+  k52_dgk_encrypt_bits<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev52, ctx->keys_dev, ctx->keys52_dev, beta, dflag, l, fb.use_table52(),
+                                                                              wide ? fb.nwin16 : fb.nwin, wide ? 16 : 8, rho, ew,
+                                                                              static_cast<double*>(scratch), out, B, queue);
+  return ctx->launched("k52_dgk_encrypt_bits");
+}
+
+template <int L29, int TPI29>
+int mont29_to_words(scb_ctx* ctx, const scb_ctx::Mod& md, const uint32_t* digits, int kw, uint32_t* out, size_t B) {
+  using C = Cfg<L29, TPI29>;
+  const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_mont29_to_words<L29, TPI29>), C::SMEM, B, C::GPB);
+  void* scratch = nullptr;
+  int rc = ctx->scratch(SC_GROUP, sizeof(uint32_t) * static_cast<size_t>(grid) * C::GPB * C::K, &scratch);
+  if (rc) return rc;
+  k_mont29_to_words<L29, TPI29><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, digits, kw, static_cast<uint32_t*>(scratch), out, B);
+  return ctx->launched("k_mont29_to_words");
+}
+
+template <int L, int TPI, int L29, int TPI29>
+int phase_step4_52(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const uint8_t* delta_a, const uint32_t* r_blind, int rb_words,
+                   const uint8_t* perm, const uint32_t* rho, int ew, int l, int do_blind, uint32_t* out, size_t B) {
+  using C = Cfg52<L, TPI>;
+  using C29 = Cfg<L29, TPI29>;
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_N];
+  const scb_ctx::FixedBase& fb = ctx->fb[0];
+  const KeysDev* hk = host_keys(ctx);
+  const int kn = hk->kn;
+  const int ubits = hk->u_bits;
+  const int wbits = window_bits_for(ubits);
+  Arena ph;
+  int rc = get_arena(ctx, SC_PHASE, 2 * pad256(sizeof(uint64_t) * B) + 2 * pad256(B) + 2 * pad256(sizeof(uint32_t) * B * kn), &ph);
+  if (rc) return rc;
+  uint64_t* alpha = ph.take<uint64_t>(B);
+  uint64_t* alpha_t = ph.take<uint64_t>(B);
+  uint8_t* r_small = ph.take<uint8_t>(B);
+  uint8_t* r_bad = ph.take<uint8_t>(B);
+  uint32_t* Tw = ph.take<uint32_t>(B * kn);
+  uint32_t* TIw = ph.take<uint32_t>(B * kn);
+  k_prep_initiator<<<static_cast<unsigned>((B + 127) / 128), 128, 0, ctx->stream>>>(ctx->keys_dev, r, l, alpha, alpha_t, r_small, r_bad, B);
+  if ((rc = ctx->launched("k_prep_initiator"))) return rc;
+  const int gridA = ctx->grid_for(reinterpret_cast<const void*>(&k52_step4_prefix<L, TPI>), C::SMEM, B, C::GPB);
+  const int gridB = ctx->grid_for(reinterpret_cast<const void*>(&k52_step4_main<L, TPI>), C::SMEM, B, C::GPB);
+  const size_t groups = static_cast<size_t>(std::max(gridA, gridB)) * C::GPB;
+  void* s4 = nullptr;
+  rc = ctx->scratch(SC_STEP4, sizeof(double) * (B + groups) * step4_scratch_doubles<L, TPI>(l, wbits), &s4);
+  if (rc) return rc;
+  k52_step4_prefix<L, TPI><<<gridA, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev52, ctx->keys_dev, db_enc, r_small, l, wbits, static_cast<double*>(s4), Tw, B);
+  if ((rc = ctx->launched("k52_step4_prefix"))) return rc;
+  // one inverse per comparison through the batched-inversion trick of the IMAD engine, handed over as canonical words
+  Arena dg;
+  rc = get_arena(ctx, SC_DIGITS, pad256(sizeof(uint32_t) * B * C29::K) + pad256(B), &dg);
+  if (rc) return rc;
+  uint32_t* TI = dg.take<uint32_t>(B * C29::K);
+  uint8_t* ok = dg.take<uint8_t>(B);
+  bool any_fail = false;
+  rc = batch_modinv_mont<L29, TPI29>(ctx, SCB_MOD_DGK_N, Tw, B, TI, ok, &any_fail);
+  if (rc) return rc;
+  if ((rc = mont29_to_words<L29, TPI29>(ctx, md, TI, kn, TIw, B))) return rc;
+  unsigned long long* queue = ctx->fresh_queue();
+  if (!queue) return fail(ctx, SCB_ECUDA, "cannot set up the work queue");
+  const bool wide = fb.table16_52 != nullptr;
+  k52_step4_main<L, TPI><<<gridB, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev52, ctx->keys_dev, ctx->keys52_dev, TIw, alpha, alpha_t, delta_a, r_blind, rb_words, perm,
+                                                                         fb.use_table52(), wide ? fb.nwin16 : fb.nwin, wide ? 16 : 8, rho, ew, l, ubits, wbits, do_blind,
+                                                                         static_cast<double*>(s4), out, B, queue);
+  if ((rc = ctx->launched("k52_step4_main"))) return rc;
+  if (any_fail) return fail(ctx, SCB_ENOTINV, "scb_initiator_step4: a DGK ciphertext has no inverse mod n");
+  return SCB_OK;
+}
+
+// K52 -> FP64 geometry, K29 -> IMAD geometry of the same modulus (they always pair up: 20/36, 30/54, 40/72, 60/108, 80/144, 120/216, 160/288)
+int dispatch_step4_52(scb_ctx* ctx, const uint32_t* db_enc, const uint32_t* r, const uint8_t* delta_a, const uint32_t* r_blind, int rb_words,
+                      const uint8_t* perm, const uint32_t* rho, int ew, int l, int do_blind, uint32_t* out, size_t B) {
+  const scb_ctx::Mod& md = ctx->mod[SCB_MOD_DGK_N];
+#define S4(L, TPI, L29, TPI29) phase_step4_52<L, TPI, L29, TPI29>(ctx, db_enc, r, delta_a, r_blind, rb_words, perm, rho, ew, l, do_blind, out, B)
+  if (md.K52 == 20 && md.K == 36) return S4(10, 2, 18, 2);
+  if (md.K52 == 30 && md.K == 54) return S4(15, 2, 27, 2);
+  if (md.K52 == 40 && md.K == 72) return S4(10, 4, 18, 4);
+  if (md.K52 == 60 && md.K == 108) return S4(15, 4, 27, 4);
+  if (md.K52 == 80 && md.K == 144) return S4(10, 8, 18, 8);
+#undef S4
+  return 1;      // no FP64 pairing for this size: the caller falls back to the IMAD kernels
+}
+
 template <int L, int TPI>
 int phase_is_zero(scb_ctx* ctx, const uint32_t* c, uint8_t* flags, size_t M) {
   using C = Cfg<L, TPI>;
@@ -876,6 +1037,11 @@ extern "C" int scb_keyholder_step4ab_dev(scb_ctx* ctx, const uint32_t* z, int l,
   k_prep_keyholder_bits<<<static_cast<unsigned>((B + 127) / 128), 128, 0, ctx->stream>>>(ctx->keys_dev, z, l, beta, dflag, B);
   if ((rc = ctx->launched("k_prep_keyholder_bits"))) return rc;
   const int K = ctx->mod[SCB_MOD_DGK_N].K;
+  if (dgk52_ready(ctx)) {
+#define CALL(L, TPI) phase_dgk_encrypt_bits52<L, TPI>(ctx, beta, dflag, l, rho, rho_words, db_enc, B)
+    SCB_DISPATCH_K52(ctx->mod[SCB_MOD_DGK_N].K52, CALL)
+#undef CALL
+  }
 #define CALL(L, TPI) phase_dgk_encrypt_bits<L, TPI>(ctx, beta, dflag, l, rho, rho_words, db_enc, B)
   SCB_DISPATCH_K(K, CALL)
 #undef CALL
@@ -889,6 +1055,10 @@ extern "C" int scb_initiator_step4_dev(scb_ctx* ctx, const uint32_t* db_enc, con
   if (!db_enc || !r || !delta_a || !c_out || l < 1 || l > MAX_L || (r_blind && rb_words <= 0) || (rho && rho_words <= 0))
     return fail(ctx, SCB_EINVAL, "scb_initiator_step4: bad argument");
   const int K = ctx->mod[SCB_MOD_DGK_N].K;
+  if (dgk52_ready(ctx)) {
+    rc = dispatch_step4_52(ctx, db_enc, r, delta_a, r_blind, rb_words, perm, rho, rho_words, l, r_blind != nullptr, c_out, B);
+    if (rc != 1) return rc;
+  }
 #define CALL(L, TPI) phase_step4<L, TPI>(ctx, db_enc, r, delta_a, r_blind, rb_words, perm, rho, rho_words, l, r_blind != nullptr, c_out, B)
   SCB_DISPATCH_K(K, CALL)
 #undef CALL

@@ -170,3 +170,26 @@ def test_malformed_messages_are_rejected_before_any_copy():
         eng.initiator_step6_7(np.zeros((3, 2, eng.kc), dtype=np.uint32), np.zeros((3, eng.kN), dtype=np.uint32), np.zeros(3, dtype=np.uint8), l)
     with pytest.raises(ValueError):
         eng.keyholder_step4j_5(np.zeros((3, l, eng.kn), dtype=np.uint32), np.zeros((3, eng.kN), dtype=np.uint32), None, l)
+
+
+@pytest.mark.parametrize("wire_format", [False, True], ids=["arrays", "packed"])
+def test_empty_and_single_comparison_through_the_drivers(wire_format):
+    """Edge batches of the interactive flow: B = 0 (every message is an empty array) and B = 1 (what the reference does)."""
+    l = 16
+    paillier, dgk = make_schemes(1024, 128, 20, l)
+    reset_engines()
+    eng = get_engine(paillier, dgk, l)
+    store = {}
+    alice = Initiator(l, DictionaryCommunicator(store, None), "bob", wire_format=wire_format)
+    bob = KeyHolder(l, DictionaryCommunicator(store, None), "alice", scheme_paillier=paillier, scheme_dgk=dgk, wire_format=wire_format)
+
+    async def run(x, y):
+        return (await asyncio.gather(alice.perform_secure_comparison(x, y), bob.perform_secure_comparison()))[0]
+
+    empty = asyncio.run(run([], []))
+    assert np.asarray(empty).shape == (0, eng.kc)
+    one = asyncio.run(run([-5], [3]))
+    assert np.asarray(one).shape == (1, eng.kc) and limbs_to_ints(eng.paillier_decrypt(one)) == [1]
+    with pytest.raises(ValueError):
+        asyncio.run(run([1, 2], [1]))                       # x and y of different lengths
+    store.clear()
