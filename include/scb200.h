@@ -162,8 +162,9 @@ enum {
   SCB_OPT_FIXED_BASE_WIDE = 2,  /* build 16-bit-window fixed-base tables (default 1; 0 = 8-bit windows only, 128x less memory) */
   SCB_OPT_SLIDING_WINDOWS = 4,  /* sliding-window programs for the shared exponents the library owns (N, CRT exponents, v_p, lambda) on the
                                    FP64 engine (default 1; 0 = fixed windows everywhere) */
-  SCB_OPT_MODEXP_FP64 = 3,      /* exponentiations with >= 64-bit exponents on the FP64-pipe multiplier (52-bit digits, exact) instead of
-                                   the IMAD one (default 1; results are bit-identical either way) */
+  SCB_OPT_MODEXP_FP64 = 3,      /* exponentiations with >= 64-bit exponents AND the DGK-side fused phases (bit encryption, steps 4c-4i) on the
+                                   FP64-pipe multiplier (52-bit digits, exact) instead of the IMAD one (default 1; results are bit-identical
+                                   either way; the 52-bit fixed-base tables are built when the DGK key is loaded with the option on) */
   SCB_OPT_SMALL_BATCH = 6,      /* FP64 engine: batches that cannot fill half of the GPU's resident groups run with 5 digits per lane on
                                    twice as many lanes per number (default 1; results are bit-identical either way) */
   SCB_OPT_SQUARE_MODULUS = 5    /* exponentiations modulo a linked square n^2 (N^2, p^2, q^2: scb_modulus_link_square) in base-n pair
