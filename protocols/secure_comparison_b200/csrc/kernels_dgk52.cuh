@@ -13,6 +13,10 @@
 
 namespace scb {
 
+// Launch bounds: 3 blocks/SM (168 registers).  Unlike the pair kernel these phases are mostly memory-to-memory products, and
+// occupancy hides their loads: 2 blocks/SM (250 registers, a healthier row-loop schedule in tools/sass_deps.py) measured
+// k52_step4_main 98 -> 116 ms and k52_dgk_encrypt_bits 26.8 -> 28.1 ms at B = 65,536 (profiles/r02k_bench_2blocks_dgk.json).
+
 // 52-bit Montgomery forms of the DGK constants the fused kernels use (device copy next to KeysDev)
 struct Keys52Dev {
   double g_m[MAXK52];           // g~
