@@ -571,6 +571,16 @@ def run_ours(args):
     plain_modulus = {"value": round(world * B / (plain_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(plain_ms, 3),
                      "bit_identical_to_pair_form": plain_same, "note": "SCB_OPT_SQUARE_MODULUS = 0: N^2, p^2, q^2 as ordinary moduli"}
 
+    # ---- and with the p and q halves of the KeyHolder's CRT forms one after the other on one stream (identical outputs)
+    eng.set_overlap_crt(False)
+    serial_ms = one_timed_pass()
+    serial_same = bool(torch.equal(ref_res, dp.res))
+    eng.set_overlap_crt(True)
+    single_stream_crt = {"value": round(world * B / (serial_ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(serial_ms, 3),
+                         "bit_identical_to_two_stream_form": serial_same,
+                         "note": "SCB_OPT_OVERLAP_CRT = 0: the q chain of every CRT encrypt / decrypt waits for the p chain "
+                                 "(kernels_ms above is measured in this order: one event stream)"}
+
     # ---- production mode: every nonce drawn on the device (ChaCha20 CSPRNG keyed from `secrets`) INSIDE the timed pass,
     #      instead of the host-supplied nonce arrays the parity path uses; checked by decrypting all result bits
     eng.rng_seed()
@@ -744,7 +754,8 @@ def run_ours(args):
                        "oracle_sample": gate, "all_ranks_green": ok_all,
                        "note": "oracle_sample = rank 0's share of the >= --parity-sample indices of the LAST TIMED step, every boundary message vs the CPU oracle"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "modexp_2048": modexp_2048, "imad_engine": imad_engine, "plain_modulus_form": plain_modulus, "device_nonces": device_nonces,
+            "modexp_2048": modexp_2048, "imad_engine": imad_engine, "plain_modulus_form": plain_modulus, "single_stream_crt": single_stream_crt,
+            "device_nonces": device_nonces,
             "modexp_4096_per_s": round(world * B / (k1_ms * 1e-3), 1) if k1_ms else None,
         }
         line.update(extra)

@@ -16,7 +16,8 @@ struct Keys52Dev;
 }  // namespace scb
 
 struct scb_ctx {
-  static constexpr int NSCRATCH = 10;
+  static constexpr int NSCRATCH = 11;
+  static constexpr int SCRATCH_AUX_GROUP = 10;   // what scratch(0, ..) hands out while the launches go to the second stream
   static constexpr int NFB = 4;
 
   struct Mod {
@@ -48,6 +49,13 @@ struct scb_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  // Second stream for the q half of the KeyHolder's CRT forms (scb200_protocol.cu, AuxLane).  An exponentiation launch ends with
+  // a drain phase -- the last tickets finish on a mostly idle GPU, about the time of one solo exponentiation -- and the p and q
+  // chains are independent, so with one chain per stream the other chain's blocks fill the SMs a draining launch gives back.
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool use_overlap = true;            // SCB_OPT_OVERLAP_CRT
+  bool on_aux = false;                // launches currently go to aux_stream (`stream` and `aux_stream` are swapped)
   std::string error;
   unsigned long long launches = 0;
   Mod mod[16];

@@ -99,6 +99,7 @@ int scb::cuda_fail(scb_ctx* ctx, cudaError_t e, const char* what) {
 
 int scb_ctx::scratch(int which, size_t bytes, void** out) {
   if (which < 0 || which >= NSCRATCH) return fail(this, SCB_EINVAL, "bad scratch index");
+  if (which == 0 && on_aux) which = SCRATCH_AUX_GROUP;      // per-group tables of a launch on the second stream
   if (scratch_bytes[which] < bytes) {
     if (scratch_ptr[which]) {
       cudaStreamSynchronize(stream);
@@ -266,6 +267,12 @@ extern "C" void scb_ctx_destroy(scb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->aux_stream) {
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
   for (auto& m : ctx->mod) {
     if (m.dev) cudaFree(m.dev);
     if (m.dev52) cudaFree(m.dev52);

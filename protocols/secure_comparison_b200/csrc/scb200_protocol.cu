@@ -415,6 +415,7 @@ extern "C" int scb_set_option(scb_ctx* ctx, int option, int value) {
     case SCB_OPT_SLIDING_WINDOWS: ctx->use_sliding = value != 0; return SCB_OK;
     case SCB_OPT_SQUARE_MODULUS: ctx->use_pair = value != 0; return SCB_OK;
     case SCB_OPT_SMALL_BATCH: ctx->use_small_batch = value != 0; return SCB_OK;
+    case SCB_OPT_OVERLAP_CRT: ctx->use_overlap = value != 0; return SCB_OK;
     case SCB_OPT_FIXED_BASE_WIDE: ctx->fb_wide = value != 0; return SCB_OK;   // takes effect at the next scb_fixed_base_load / scb_dgk_set_public
     default: return fail(ctx, SCB_EINVAL, "scb_set_option: unknown option %d", option);
   }
@@ -946,21 +947,64 @@ int phase_crt_decrypt_combine(scb_ctx* ctx, const uint32_t* Lq, uint32_t* out, s
   return ctx->launched("k_crt_decrypt_combine");
 }
 
+// The launches issued while an AuxLane is alive go to the context's second stream (with their own per-group scratch), ordered
+// after everything the main stream held when fork() was called; the destructor makes the main stream wait for them.  Used
+// for the q half of the CRT forms below: the p and q chains are independent, and a launch of one chain fills the SMs that a
+// draining launch of the other gives back (the last tickets of an exponentiation launch otherwise finish on a mostly idle
+// GPU).  Off while per-kernel timing is on (one event stream) and with SCB_OPT_OVERLAP_CRT = 0.
+struct AuxLane {
+  scb_ctx* ctx;
+  bool on = false;
+  static bool fork(scb_ctx* ctx) {
+    if (!ctx->use_overlap || ctx->profiling) return false;
+    if (!ctx->aux_stream) {
+      cudaStream_t st = nullptr;
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+        if (st) cudaStreamDestroy(st);
+        if (a) cudaEventDestroy(a);
+        cudaGetLastError();
+        return false;
+      }
+      ctx->aux_stream = st;
+      ctx->ev_fork = a;
+      ctx->ev_join = b;
+    }
+    return cudaEventRecord(ctx->ev_fork, ctx->stream) == cudaSuccess && cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0) == cudaSuccess;
+  }
+  AuxLane(scb_ctx* c, bool forked) : ctx(c), on(forked) {
+    if (!on) return;
+    std::swap(ctx->stream, ctx->aux_stream);
+    ctx->on_aux = true;
+  }
+  ~AuxLane() {
+    if (!on) return;
+    std::swap(ctx->stream, ctx->aux_stream);
+    ctx->on_aux = false;
+    cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+  }
+};
+
 // KeyHolder with the factorisation: (1 + m N) * rho^N mod N^2 through p, p^2, q, q^2 (see kernels_protocol.cuh)
 int paillier_encrypt_crt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M) {
   const KeysDev* hk = host_keys(ctx);
   const int kN = hk->kN, kP = hk->kP;
   Arena ph;
-  int rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * M * kP) + 2 * pad256(sizeof(uint32_t) * M * kN), &ph);
+  int rc = get_arena(ctx, SC_CRT, 2 * pad256(sizeof(uint32_t) * M * kP) + 2 * pad256(sizeof(uint32_t) * M * kN), &ph);
   if (rc) return rc;
-  uint32_t* b = ph.take<uint32_t>(M * kP);
+  uint32_t* b[2] = {ph.take<uint32_t>(M * kP), ph.take<uint32_t>(M * kP)};
   uint32_t* s[2] = {ph.take<uint32_t>(M * kN), ph.take<uint32_t>(M * kN)};
   const int slotP[2] = {SCB_MOD_PAILLIER_P, SCB_MOD_PAILLIER_Q}, slotP2[2] = {SCB_MOD_PAILLIER_P2, SCB_MOD_PAILLIER_Q2};
-  for (int h = 0; h < 2; h++) {
+  const bool forked = AuxLane::fork(ctx);
+  for (int h = 0; h < 2 && rc == SCB_OK; h++) {
+    AuxLane lane(ctx, forked && h == 1);
     const uint32_t* ex = ctx->crt_exp_dev + static_cast<size_t>(3 * h) * kP;
-    if ((rc = scb::modexp_dev_ex(ctx, slotP[h], rho, kN, ex, kP, ctx->crt_e1_bits[h], b, kP, M))) return rc;          // (rho mod P)^(Q mod (P-1)) mod P
-    if ((rc = scb::modexp_dev_ex(ctx, slotP2[h], b, kP, ex + kP, kP, ctx->crt_P_bits[h], s[h], kN, M))) return rc;    // b^P mod P^2
+    rc = scb::modexp_dev_ex(ctx, slotP[h], rho, kN, ex, kP, ctx->crt_e1_bits[h], b[h], kP, M);                         // (rho mod P)^(Q mod (P-1)) mod P
+    if (rc == SCB_OK) rc = scb::modexp_dev_ex(ctx, slotP2[h], b[h], kP, ex + kP, kP, ctx->crt_P_bits[h], s[h], kN, M);  // b^P mod P^2
   }
+  if (rc) return rc;
   const int K = ctx->mod[SCB_MOD_PAILLIER_N2].K;
 #define CALL(L, TPI) phase_crt_encrypt_combine<L, TPI>(ctx, s[0], s[1], plain, out, M)
   SCB_DISPATCH_K(K, CALL)
@@ -976,10 +1020,13 @@ int paillier_decrypt_crt(scb_ctx* ctx, const uint32_t* c, uint32_t* out, size_t 
   uint32_t* y = ph.take<uint32_t>(2 * M * kN);
   uint32_t* Lq = ph.take<uint32_t>(2 * M * kP);
   const int slotP2[2] = {SCB_MOD_PAILLIER_P2, SCB_MOD_PAILLIER_Q2};
-  for (int h = 0; h < 2; h++) {
+  const bool forked = AuxLane::fork(ctx);
+  for (int h = 0; h < 2 && rc == SCB_OK; h++) {
+    AuxLane lane(ctx, forked && h == 1);
     const uint32_t* ex = ctx->crt_exp_dev + static_cast<size_t>(3 * h + 2) * kP;
-    if ((rc = scb::modexp_dev_ex(ctx, slotP2[h], c, 2 * kN, ex, kP, ctx->crt_P_bits[h], y + static_cast<size_t>(h) * M * kN, kN, M))) return rc;   // c^(P-1) mod P^2
+    rc = scb::modexp_dev_ex(ctx, slotP2[h], c, 2 * kN, ex, kP, ctx->crt_P_bits[h], y + static_cast<size_t>(h) * M * kN, kN, M);   // c^(P-1) mod P^2
   }
+  if (rc) return rc;
   k_crt_L<<<static_cast<unsigned>((2 * M + 63) / 64), 64, 0, ctx->stream>>>(ctx->keys_dev, y, Lq, M);
   if ((rc = ctx->launched("k_crt_L"))) return rc;
   const int K = ctx->mod[SCB_MOD_PAILLIER_N].K;

@@ -168,6 +168,10 @@ class Engine:
         """Small batches on twice the lanes per number (default) or always the 10-digits-per-lane geometry; bit-identical results."""
         self._check(self.lib.scb_set_option(self.ctx, nat.OPT_SMALL_BATCH, int(bool(enabled))))
 
+    def set_overlap_crt(self, enabled: bool) -> None:
+        """The p and q halves of the KeyHolder's CRT forms on two streams (default) or one after the other; bit-identical results."""
+        self._check(self.lib.scb_set_option(self.ctx, nat.OPT_OVERLAP_CRT, int(bool(enabled))))
+
     def modulus(self, slot: int) -> int:
         return self._moduli[slot][0]
 

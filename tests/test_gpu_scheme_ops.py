@@ -77,6 +77,35 @@ def test_paillier_crt_and_public_formulas_agree(setup):
         eng.set_sliding_windows(True)
 
 
+def test_crt_halves_on_two_streams_are_bit_identical(setup):
+    """SCB_OPT_OVERLAP_CRT: the q half of the CRT forms runs on the context's second stream.  Back-to-back calls (buffers
+    reused across the fork / join) give the same bits as the single-stream order and as the closed forms."""
+    paillier, dgk, l, eng, oracle, rng = setup
+    N, N2 = paillier.public_key.n, paillier.public_key.n_squared
+    B = 1500                                          # several warps per launch on both streams
+    m = [rng.randrange(N) for _ in range(B)]
+    rho = [rng.randrange(1, N) for _ in range(B)]
+    M, RHO = ints_to_limbs(m, eng.kN), ints_to_limbs(rho, eng.kN)
+    outs = {}
+    try:
+        for overlap in (True, False, True):
+            eng.set_overlap_crt(overlap)
+            c1 = eng.paillier_encrypt(M, RHO)
+            d1 = eng.paillier_decrypt(c1)             # consumes c1 right after the join
+            c2 = eng.paillier_encrypt(d1, RHO)        # same plaintexts again
+            outs.setdefault(overlap, []).append((c1.copy(), d1.copy(), c2.copy()))
+    finally:
+        eng.set_overlap_crt(True)
+    ref = outs[False][0]
+    for trip in outs[True]:
+        for got, want in zip(trip, ref):
+            assert np.array_equal(got, want)
+    assert np.array_equal(ref[0], ref[2])
+    assert limbs_to_ints(ref[1]) == m
+    idx = [0, 1, B // 2, B - 1]
+    assert [limbs_to_ints(ref[0])[i] for i in idx] == [(1 + m[i] * N) * pow(rho[i], N, N2) % N2 for i in idx]
+
+
 def test_step1_pieces(setup):
     paillier, dgk, l, eng, oracle, rng = setup
     N, N2 = paillier.public_key.n, paillier.public_key.n_squared
