@@ -68,6 +68,7 @@ __device__ __forceinline__ uint64_t raw(double d) { return static_cast<uint64_t>
 // All 32 lanes of the warp must call this together.
 template <int L, int TPI>
 __device__ __forceinline__ void resolve_carries(uint64_t (&col)[L], uint64_t hi_of_last, double (&r)[L]) {
+  static_assert(L >= 2, "resolve_carries: a lane holds at least two digits");
   const int t = (threadIdx.x & 31) % TPI;
   // within the lane: d[p] = low 52 bits, carry on; `hi_of_last` joins the carry leaving the lane (weight 2^(52 L))
   uint64_t c = 0;
@@ -83,32 +84,36 @@ __device__ __forceinline__ void resolve_carries(uint64_t (&col)[L], uint64_t hi_
   if (t == 0) cin = 0;
   uint64_t s = col[0] + (cin & MASK52);
   col[0] = s & MASK52;
-  uint64_t k = (s >> 52) + (cin >> 52);
-#pragma unroll
-  for (int p = 1; p < L; p++) {
-    s = col[p] + k;
-    col[p] = s & MASK52;
-    k = s >> 52;
-  }
-  // second-order carries (0 or 1 leaving a lane): needs another round only when a lane's digits are all ones
+  s = col[1] + (s >> 52) + (cin >> 52);
+  col[1] = s & MASK52;
+  uint64_t k = s >> 52;
+  // What is left is a carry of 0 or 1 out of digit 1: it moves on only through digits that are all ones (about 2^-46 per
+  // lane and product on random data), so the common case ends here; the loop ripples it through the rest of the lane, then
+  // lane by lane from digit 0 (warp-uniform trip count; driven by test_fp64_engine_carry_resolution_rare_paths).
+  // Measured at B = 65,536 against an unconditional second sweep: 1.0-1.5 % on every exponentiation kernel; a carry-save
+  // first step (all columns split at once, depth independent of L) measured 0.5-2 % slower than this form.
+  int from = 2;
   while (__any_sync(FULL, k != 0)) {
+#pragma unroll
+    for (int p = 0; p < L; p++) {
+      if (p >= from) {
+        s = col[p] + k;
+        col[p] = s & MASK52;
+        k = s >> 52;
+      }
+    }
     uint64_t kin = __shfl_up_sync(FULL, k, 1, TPI);
     if (t == 0) kin = 0;
     k = kin;
-#pragma unroll
-    for (int p = 0; p < L; p++) {
-      s = col[p] + k;
-      col[p] = s & MASK52;
-      k = s >> 52;
-    }
+    from = 0;
   }
 #pragma unroll
   for (int p = 0; p < L; p++) r[p] = u52_to_double(col[p]);
 }
 
 // ---- the row loop -------------------------------------------------------------------------------------------------
-constexpr int PASS_SAVE = 1;     // store the complemented quotient digits of this pass (pair arithmetic, pass 1)
-constexpr int PASS_INJECT = 2;   // add the stored complement (+1) into the low column of every row (pair arithmetic, pass 2)
+constexpr int PASS_SAVE = 1;     // pass 1 of the pair arithmetic: its quotient digits are what pass 2 reads (every PAIR pass stores them)
+constexpr int PASS_INJECT = 2;   // start the accumulator from R - m, m = the stored quotient digits (pair arithmetic, pass 2)
 
 // The row loop of one Montgomery product on register operands, returning the UNRESOLVED columns:
 //   sum_p col[p] 2^(52 p) + hi_last 2^(52 L)  (per lane)  =  this lane's share of (a * b [+ R - m] + q n) / R
@@ -131,7 +136,7 @@ __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const doubl
   const int t = (threadIdx.x & 31) % TPI;
   const bool top = t == TPI - 1;
   const bool low_lane = t == 0;
-  const bool save = PAIR && (flags & PASS_SAVE) != 0, inject = PAIR && (flags & PASS_INJECT) != 0;
+  const bool inject = PAIR && (flags & PASS_INJECT) != 0;
   const double C1 = SCB_2P104, C12 = SCB_2P104 + SCB_2P52;
   // Exponent bookkeeping: every raw hi carries BITS_2P104 and every raw lo BITS_2P52 on top of its mantissa.  A column
   // receives exactly 2 of each per row while it is in this lane, so the total is subtracted up front (mod 2^64): the
@@ -142,7 +147,16 @@ __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const doubl
     AL[i] = 0ull - 2ull * (i + 1) * BITS_2P52;
     AH[i] = 0ull - 2ull * (i + 1) * BITS_2P104;
   }
-  if (PAIR && inject && low_lane) AL[0] += 1ull;           // the "+ 1" of R - m = complement(m) + 1
+  if (PAIR && inject) {
+    // R - m = complement(m) + 1 enters as the accumulator's initial value: digit j of the complement in column j (it is
+    // summed into the quotient digit of row j like every product that lands there).  L conversions per lane and pass
+    // instead of one load + add in every row.
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < L; i++) AL[i] += double_to_u52(__longlong_as_double(static_cast<long long>(sm_q[(t * L + i) * GPW]))) ^ MASK52;
+    if (low_lane) AL[0] += 1ull;
+    __syncwarp();
+  }
   const double* bp = sm_stream;
   uint64_t* qp = sm_q;
   double bj = bp[0];
@@ -159,10 +173,6 @@ __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const doubl
         AH[rr % L] += raw(hi);
         AL[rr % L] += raw(lo);
       }
-      if (PAIR && inject) {
-        const uint64_t c = qp[0];                  // complement digit j of the previous pass's quotient
-        if (low_lane) AL[rr % L] += c;
-      }
       // quotient digit: q = (column 0 mod 2^52) * n' mod 2^52 (the outstanding exponent constants have zero low bits)
       const double v0 = u52_to_double(AL[rr % L] & MASK52);
       const double qh = __fma_rz(v0, np, C1);
@@ -173,10 +183,13 @@ __device__ __forceinline__ void mmd_rows_core(const double (&av)[L], const doubl
 #ifdef SCB_EXP_NO_CHAIN
       q = bnext;                                   /* experiment (tools/rowloop_microbench.cu): no serial quotient chain */
 #endif
-      if (PAIR && save) {
-        if (low_lane) qp[0] = double_to_u52(q) ^ MASK52;
+      if (PAIR) {
+        // every pass stores its quotient digits (as the doubles they are; nobody reads what passes 2 and 3 leave), so the
+        // loop has no flag-dependent branch: with `if (save)` ptxas put real branches between the rows and the launch of
+        // the B randomizers went from 333 to 344 ms
+        if (low_lane) qp[0] = raw(q);
+        qp += GPW;
       }
-      if (PAIR) qp += GPW;
 #pragma unroll
       for (int i = 1; i < L; i++) {
         const double hi = __fma_rz(av[i], bj, C1);

@@ -40,7 +40,7 @@ struct GeoPair {
   static constexpr int K = L * TPI;
   static constexpr int GPW = 32 / TPI;
   static constexpr int S2_OFF = (K + 1) * GPW;           // second streamed-operand area (each: K digits + the prefetch pad row)
-  static constexpr int Q_OFF = 2 * (K + 1) * GPW;        // complemented quotient digits of pass 1 (uint64, K of them)
+  static constexpr int Q_OFF = 2 * (K + 1) * GPW;        // quotient digits of pass 1 (K doubles, stored as their bit patterns)
   static constexpr int WARP_SMEM_WORDS64 = (3 * K + 2) * GPW;
 };
 
