@@ -13,9 +13,11 @@
 
 namespace scb {
 
-// Launch bounds: 3 blocks/SM (168 registers).  Unlike the pair kernel these phases are mostly memory-to-memory products, and
-// occupancy hides their loads: 2 blocks/SM (250 registers, a healthier row-loop schedule in tools/sass_deps.py) measured
-// k52_step4_main 98 -> 116 ms and k52_dgk_encrypt_bits 26.8 -> 28.1 ms at B = 65,536 (profiles/r02k_bench_2blocks_dgk.json).
+// Launch bounds.  Unlike the pair kernel these phases are mostly memory-to-memory products, and occupancy hides their loads:
+// 2 blocks/SM (250 registers, a healthier row-loop schedule in tools/sass_deps.py) measured k52_step4_main 98 -> 116 ms and
+// k52_dgk_encrypt_bits 26.8 -> 28.1 ms at B = 65,536 (profiles/r02k_bench_2blocks_dgk.json); 4 blocks/SM (128 registers, a
+// few spills) measured k52_step4_main 97.7 -> 93.8 ms but k52_dgk_encrypt_bits 27.0 -> 29.0 ms (profiles/r02t_bounds.log).
+// Hence: 4 for k52_step4_main, 3 for the others.
 
 // 52-bit Montgomery forms of the DGK constants the fused kernels use (device copy next to KeysDev)
 struct Keys52Dev {
@@ -103,7 +105,7 @@ k52_step4_prefix(const Modulus52Dev* __restrict__ m, const KeysDev* __restrict__
 
 // pass B: everything else.  TIw: the inverse of the total product as canonical words ([B][kn]).
 template <int L, int TPI>
-__global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 3 : 2))
+__global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 4 : 2))
 k52_step4_main(const Modulus52Dev* __restrict__ m, const KeysDev* __restrict__ keys, const Keys52Dev* __restrict__ k52, const uint32_t* __restrict__ TIw,
                const uint64_t* __restrict__ alpha, const uint64_t* __restrict__ alpha_tilde, const uint8_t* __restrict__ delta_a,
                const uint32_t* __restrict__ r_blind, int rb_words, const uint8_t* __restrict__ perm, const double* fb_table, int nwin, int fbw,

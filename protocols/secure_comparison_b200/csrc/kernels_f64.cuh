@@ -259,6 +259,7 @@ __global__ void k_debug_resolve52(const uint64_t* __restrict__ cols, const uint6
 // out[i] = (mul_in[i] *) base[i]^exp[i] mod n
 // registers: L = 10 needs ~150 (3 blocks of 128 threads per SM: measured 3 % faster than 4 blocks with a few spills),
 // L = 15 needs ~230 (2 blocks per SM)
+// (2 blocks / 255 registers: the 1024-bit launches unchanged, the is-zero launch 50.9 -> 53.3 ms: profiles/r02t_bounds.log)
 template <int L, int TPI>
 __global__ void __launch_bounds__(BLOCK_THREADS, (L <= 10 ? 3 : 2))
 k_modexp52(const Modulus52Dev* __restrict__ m, const uint32_t* __restrict__ base, int kbase, const uint32_t* __restrict__ exp, int ewords,

@@ -44,6 +44,11 @@ struct GeoPair {
   static constexpr int WARP_SMEM_WORDS64 = (3 * K + 2) * GPW;
 };
 
+// Measured and not kept (profiles/r02u_dual.log): a window product in TWO passes, the second one accumulating a d + b c +
+// (R - m) with a single reduction (5 K^2 digit products instead of 6 K^2; tests/pairmul_model.py, mul_dual, bounds hold).
+// Bit-identical, no spills -- and 20 % SLOWER on both launches (333 -> 399 ms, 91 -> 111 ms): the second unrolled row loop
+// (28 KB of code next to the 20 KB of the first) no longer fits the instruction cache the two hot loops alternate in.
+//
 // The row loop with the two hooks of the pair arithmetic: bn52.cuh, mmd_rows_core<L, TPI, true>.
 template <int L, int TPI>
 __device__ __forceinline__ void mmd_rows_pair(const double (&av)[L], const double (&nv)[L], const double np, const double* __restrict__ sm_stream,

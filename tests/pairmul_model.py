@@ -94,6 +94,30 @@ class PairCtx:
         s2, _ = self.redc_pass(b, c)
         return self.norm(t), self.norm(s1 + s2 + n - 1)
 
+    def redc_pass_dual(self, a, stream_a, b, stream_b, comp):
+        """(a * stream_a + b * stream_b + R - m) R^-1 mod n in ONE K-row pass (one reduction for both products): the form
+        the exponentiation kernel uses for window products (mmd_rows_dual)."""
+        K, n = self.K, self.n
+        sa, sb = digits(stream_a, K), digits(stream_b, K)
+        T = 0
+        for j in range(K):
+            T += a * sa[j] + b * sb[j] + comp[j] + (1 if j == 0 else 0)
+            qj = ((T & MASK) * self.np) & MASK
+            T += qj * n
+            assert T & MASK == 0
+            T >>= W
+        return T
+
+    def mul_dual(self, x, y):
+        """Same value as mul() with two passes: t = REDC(a c), s = REDC(a d + b c + (R - m)) + (n - 1)."""
+        (a, b), (c, d) = x, y
+        n = self.n
+        assert max(a, b, c, d) < 4 * n
+        t, m = self.redc_pass(a, c)
+        comp = [MASK - mj for mj in m]
+        s = self.redc_pass_dual(a, d, b, c, comp)
+        return self.norm(t), self.norm(s + n - 1)
+
     def value(self, x):
         return (x[0] + x[1] * self.n) % self.n2
 

@@ -35,3 +35,19 @@ def test_pair_modexp_sliding_program(bits, ebits):
     prog, w = compile_program_py(e)
     for x in (0, 1, n - 1, n * n - 1, rng.randrange(n * n), rng.randrange(n)):
         assert ctx.modexp_prog(x, prog, w, 64 * ((bits + 31) // 32)) == pow(x, e, n * n)
+
+
+def test_two_pass_window_product_of_the_model():
+    """mul_dual (a d + b c + (R - m) reduced ONCE) equals mul and keeps the (2n, 4n) bounds, also at the two sizes with the
+    least Montgomery slack.  The kernel keeps the three-pass form (kernels_f64_pair.cuh explains why); the model pins the
+    algebra of the alternative."""
+    rng = random.Random(11)
+    for bits in (1024, 1036, 2048, 2076):
+        n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
+        ctx = PairCtx(n)
+        for it in range(40):
+            x = (rng.randrange(4 * n), rng.randrange(4 * n)) if it else (4 * n - 1, 4 * n - 1)
+            y = (rng.randrange(4 * n), rng.randrange(4 * n)) if it else (4 * n - 1, 4 * n - 1)
+            r = ctx.mul_dual(x, y)
+            assert ctx.value(r) == ctx.value(ctx.mul(x, y))
+            assert r[0] < 2 * n + 1 and r[1] < 4 * n
