@@ -4,7 +4,7 @@
 //
 // Same algorithms, same data flow and the same warp-uniformity rules as their IMAD-engine twins in kernels_generic.cuh /
 // kernels_protocol.cuh (k_fb_*, k_dgk_encrypt_bits, k_step4_prefix, k_step4_main) -- digits are 52-bit integers held in
-// doubles, products are mmd() (memory to memory) and the register-resident group_modexp52().  The FP64 engine multiplies
+// doubles, every product is mmd() (memory to memory; one copy of the row loop per kernel).  The FP64 engine multiplies
 // 1.36x faster than the IMAD one, and with the Paillier exponentiations in pair form these phases had grown to 14 % of a
 // pass.  SCB_OPT_MODEXP_FP64 = 0 keeps everything on the IMAD kernels (bit-identical; bench.py compares the two every run).
 #pragma once
@@ -17,7 +17,8 @@ namespace scb {
 // 2 blocks/SM (250 registers, a healthier row-loop schedule in tools/sass_deps.py) measured k52_step4_main 98 -> 116 ms and
 // k52_dgk_encrypt_bits 26.8 -> 28.1 ms at B = 65,536 (profiles/r02k_bench_2blocks_dgk.json); 4 blocks/SM (128 registers, a
 // few spills) measured k52_step4_main 97.7 -> 93.8 ms but k52_dgk_encrypt_bits 27.0 -> 29.0 ms (profiles/r02t_bounds.log).
-// Hence: 4 for k52_step4_main, 3 for the others.
+// Hence: 4 for k52_step4_main, 3 for the others.  (With the single-copy form of step 4i, below: 3 / 4 / 5 blocks per SM =
+// 90.2 / 84.6 / 126 ms -- at 5 the row loop spills; profiles/r02x_step4_blocks.log.)
 
 // 52-bit Montgomery forms of the DGK constants the fused kernels use (device copy next to KeysDev)
 struct Keys52Dev {
@@ -52,6 +53,31 @@ k52_dgk_encrypt_bits(const Modulus52Dev* __restrict__ m, const KeysDev* __restri
     if (rho != nullptr) group_fixed_base_mul52<L, TPI>(m, sm_group, ACC, fb_table, nwin, rho + idx * ew, ew, fbw);
     mmd<L, TPI>(m, sm_group, TMP, ACC, m->unit);
     canonical_store52<L, TPI>(m, sm_group, TMP, out + idx * kn, kn, active);
+  }
+}
+
+// acc = x~^e (fixed windows, per-group exponent) through memory-to-memory products only: the same operation sequence for
+// every group of the warp (a zero window multiplies by 1~).  acc, xm: K-digit slots; table: (1 << wbits) slots.
+// Used for the short blinding exponents of step 4i INSTEAD of the register-resident group_modexp52(): that one inlines a
+// second 20 KB copy of the unrolled row loop next to mmd()'s, and a kernel that alternates between two such bodies runs out of
+// instruction cache -- k52_step4_main 93.8 -> 84.6 ms at B = 65,536 with this single-copy form although each product now
+// goes through memory (profiles/r02w_step4_mem.log; the same effect, in the other direction, as profiles/r02u_dual.log).
+template <int L, int TPI>
+__device__ __forceinline__ void group_modexp52_mem(const Modulus52Dev* __restrict__ m, double* sm_group, double* acc, const double* xm,
+                                                   const uint32_t* __restrict__ e, int ewords, int ebits, int wbits, double* table) {
+  constexpr int K = Geo52<L, TPI>::K;
+  const int nwin = (ebits + wbits - 1) / wbits;
+  if (nwin == 0) {
+    copy52<L, TPI>(acc, m->one);
+    return;
+  }
+  copy52<L, TPI>(table, m->one);
+  copy52<L, TPI>(table + K, xm);
+  for (int v = 2; v < (1 << wbits); v++) mmd<L, TPI>(m, sm_group, table + static_cast<size_t>(v) * K, table + static_cast<size_t>(v - 1) * K, xm);
+  copy52<L, TPI>(acc, table + static_cast<size_t>(get_bits(e, ewords, (nwin - 1) * wbits, wbits)) * K);
+  for (int wi = nwin - 2; wi >= 0; wi--) {
+    for (int s = 0; s < wbits; s++) mmd<L, TPI>(m, sm_group, acc, acc, acc);
+    mmd<L, TPI>(m, sm_group, acc, acc, table + static_cast<size_t>(get_bits(e, ewords, wi * wbits, wbits)) * K);
   }
 }
 
@@ -176,7 +202,7 @@ k52_step4_main(const Modulus52Dev* __restrict__ m, const KeysDev* __restrict__ k
       const double* Cs = Cm + static_cast<size_t>(src) * K;
       const double* res = Cs;
       if (do_blind) {
-        group_modexp52<L, TPI>(m, sm_group, T, Cs, r_blind + (i * (l + 1) + src) * rb_words, rb_words, ubits, wbits, table);
+        group_modexp52_mem<L, TPI>(m, sm_group, T, Cs, r_blind + (i * (l + 1) + src) * rb_words, rb_words, ubits, wbits, table);
         res = T;
       }
       if (rho != nullptr) {
