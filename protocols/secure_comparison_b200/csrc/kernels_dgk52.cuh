@@ -59,9 +59,10 @@ k52_dgk_encrypt_bits(const Modulus52Dev* __restrict__ m, const KeysDev* __restri
 // acc = x~^e (fixed windows, per-group exponent) through memory-to-memory products only: the same operation sequence for
 // every group of the warp (a zero window multiplies by 1~).  acc, xm: K-digit slots; table: (1 << wbits) slots.
 // Used for the short blinding exponents of step 4i INSTEAD of the register-resident group_modexp52(): that one inlines a
-// second 20 KB copy of the unrolled row loop next to mmd()'s, and a kernel that alternates between two such bodies runs out of
-// instruction cache -- k52_step4_main 93.8 -> 84.6 ms at B = 65,536 with this single-copy form although each product now
-// goes through memory (profiles/r02w_step4_mem.log; the same effect, in the other direction, as profiles/r02u_dual.log).
+// second 20 KB copy of the unrolled row loop next to mmd()'s, and this kernel alternates between the two all the time:
+// k52_step4_main 93.8 -> 84.6 ms at B = 65,536 with this single-copy form although each product now goes through memory
+// (profiles/r02w_step4_mem.log).  Most likely instruction-cache capacity (the opposite experiment: profiles/r02u_dual.log);
+// not confirmed with a counter.
 template <int L, int TPI>
 __device__ __forceinline__ void group_modexp52_mem(const Modulus52Dev* __restrict__ m, double* sm_group, double* acc, const double* xm,
                                                    const uint32_t* __restrict__ e, int ewords, int ebits, int wbits, double* table) {

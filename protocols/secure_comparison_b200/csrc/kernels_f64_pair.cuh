@@ -46,8 +46,10 @@ struct GeoPair {
 
 // Measured and not kept (profiles/r02u_dual.log): a window product in TWO passes, the second one accumulating a d + b c +
 // (R - m) with a single reduction (5 K^2 digit products instead of 6 K^2; tests/pairmul_model.py, mul_dual, bounds hold).
-// Bit-identical, no spills -- and 20 % SLOWER on both launches (333 -> 399 ms, 91 -> 111 ms): the second unrolled row loop
-// (28 KB of code next to the 20 KB of the first) no longer fits the instruction cache the two hot loops alternate in.
+// Bit-identical, no spills -- and 20 % SLOWER on both launches (333 -> 399 ms, 91 -> 111 ms) although only a fifth of the
+// passes changed.  The likely cause is code size: a second unrolled row loop (28 KB next to the 20 KB of the first) in a
+// main loop whose hot code is already ~35-40 KB; k52_step4_main showed the same sensitivity in the other direction
+// (kernels_dgk52.cuh, group_modexp52_mem).  Not confirmed with an instruction-cache counter.
 //
 // The row loop with the two hooks of the pair arithmetic: bn52.cuh, mmd_rows_core<L, TPI, true>.
 template <int L, int TPI>
