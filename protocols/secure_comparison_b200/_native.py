@@ -21,6 +21,8 @@ OPT_SLIDING_WINDOWS = 4
 OPT_SQUARE_MODULUS = 5
 OPT_SMALL_BATCH = 6
 OPT_OVERLAP_CRT = 7
+PEAK_IMAD_WIDE = 0
+PEAK_DFMA = 1
 RNG_BELOW, RNG_BITS, RNG_COINS, RNG_PERMUTATIONS, RNG_BLOCK = 0, 1, 2, 3, 4
 SCB_OK, SCB_EINVAL, SCB_ECUDA, SCB_ENOMEM, SCB_ENOTINV, SCB_ESTATE = 0, -1, -2, -3, -4, -5
 

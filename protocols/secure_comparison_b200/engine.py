@@ -76,7 +76,7 @@ class Engine:
     def measure_peak(self, which: str) -> float:
         """Issue-rate ceiling of a multiplier pipe measured on this GPU, thread-level ops/s: ``"imad_wide"`` or ``"dfma"``."""
         out = ctypes.c_double(0.0)
-        self._check(self.lib.scb_measure_peak(self.ctx, {"imad_wide": 0, "dfma": 1}[which], ctypes.byref(out)))
+        self._check(self.lib.scb_measure_peak(self.ctx, {"imad_wide": nat.PEAK_IMAD_WIDE, "dfma": nat.PEAK_DFMA}[which], ctypes.byref(out)))
         return float(out.value)
 
     def profile_begin(self) -> None:

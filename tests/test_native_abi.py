@@ -30,6 +30,18 @@ def test_library_is_built_and_exports_every_declared_symbol():
     assert lib.scb_version() >= 100
 
 
+def test_option_and_slot_constants_match_the_header():
+    """Every SCB_OPT_* / SCB_PEAK_* enumerator of include/scb200.h has the same value in the ctypes binding."""
+    text = open(os.path.join(ROOT, "include", "scb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = {name: int(val) for name, val in re.findall(r"\b(SCB_(?:OPT|PEAK)_[A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    assert len([k for k in enums if k.startswith("SCB_OPT_")]) >= 7
+    for name, val in enums.items():
+        py = name[len("SCB_"):]
+        assert hasattr(nat, py), f"_native.py lacks {py}"
+        assert getattr(nat, py) == val, name
+
+
 def test_limb_round_trip():
     rng = random.Random(0)
     vals = [0, 1, (1 << 2048) - 1] + [rng.getrandbits(2048) for _ in range(20)]
