@@ -135,6 +135,9 @@ int scb_fixed_base_exp_dev(scb_ctx* ctx, int tslot, const uint32_t* exp, int exp
  * on crafted column values.  cols: [G][40] column sums (< 2^63), hi: [G][4] extra high accumulator per lane, out: [G][40]
  * normalised 52-bit digits.  Its second-order ripple path is unreachable with random operands, so tests drive it here. */
 int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G);
+/* the same hook for any geometry the FP64 engine instantiates: digits_per_lane x lanes in {10x2, 10x4, 10x8, 10x16, 5x4, 5x8,
+ * 5x16, 15x2, 15x4, 15x8}; cols [G][K], hi [G][lanes], out [G][K] with K = digits_per_lane * lanes */
+int scb_debug_resolve52_geo(scb_ctx* ctx, int digits_per_lane, int lanes, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G);
 
 /* Test hook, host only (no GPU): the sliding-window program the library compiles for a shared exponent.  Returns the number
  * of entries written (0 = the exponent is below 2^63 and stays on the fixed-window loop), negative on error.

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "scb_dgk_set_private": ([_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "scb_debug_compile_exponent": ([_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)], ctypes.c_int),
     "scb_debug_resolve52": ([_vp, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
+    "scb_debug_resolve52_geo": ([_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_rng_seed": ([_vp, _vp, _vp], ctypes.c_int),
     "scb_rng_below_dev": ([_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),
     "scb_rng_bits_dev": ([_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_size_t], ctypes.c_int),

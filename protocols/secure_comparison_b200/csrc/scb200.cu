@@ -938,12 +938,13 @@ extern "C" int scb_modinv_dev(scb_ctx* ctx, int slot, const uint32_t* a, uint32_
   return modinv_dev_raw(ctx, slot, a, out, ok, B);
 }
 
-// test hook: carry resolution of the FP64 engine on crafted column values (K = 40: 10 digits x 4 lanes)
-extern "C" int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G) {
+// test hook: carry resolution of the FP64 engine on crafted column values, in any geometry the engine instantiates
+// (digits per lane x lanes per number); cols [G][K], hi [G][lanes], out [G][K], K = digits_per_lane * lanes
+extern "C" int scb_debug_resolve52_geo(scb_ctx* ctx, int digits_per_lane, int lanes, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G) {
   if (!ctx || !cols || !hi || !out) return SCB_EINVAL;
   if (G == 0) return SCB_OK;
   cudaSetDevice(ctx->device);
-  constexpr int K = 40, TPI = 4;
+  const int K = digits_per_lane * lanes, TPI = lanes;
   void* dev = nullptr;
   const size_t nb_cols = sizeof(uint64_t) * G * K, nb_hi = sizeof(uint64_t) * G * TPI;
   int rc = ctx->scratch(2, 2 * nb_cols + nb_hi + 1024, &dev);
@@ -954,11 +955,22 @@ extern "C" int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uin
   cudaError_t e = cudaMemcpyAsync(dcols, cols, nb_cols, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dhi, hi, nb_hi, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D copy");
-  k_debug_resolve52<10, 4><<<1, 32, 0, ctx->stream>>>(dcols, dhi, dout, G);
+#define GEO(L_, T_)                                                                         \
+  if (digits_per_lane == L_ && lanes == T_) {                                               \
+    k_debug_resolve52<L_, T_><<<1, 32, 0, ctx->stream>>>(dcols, dhi, dout, G);              \
+  } else
+  GEO(10, 2) GEO(10, 4) GEO(10, 8) GEO(10, 16) GEO(5, 4) GEO(5, 8) GEO(5, 16) GEO(15, 2) GEO(15, 4) GEO(15, 8)
+  return fail(ctx, SCB_EINVAL, "scb_debug_resolve52_geo: geometry %d x %d is not one the engine uses", digits_per_lane, lanes);
+#undef GEO
   if ((rc = ctx->launched("k_debug_resolve52"))) return rc;
   e = cudaMemcpyAsync(out, dout, nb_cols, cudaMemcpyDeviceToHost, ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H copy");
   return scb_sync(ctx);
+}
+
+// the same for K = 40: 10 digits x 4 lanes
+extern "C" int scb_debug_resolve52(scb_ctx* ctx, const uint64_t* cols, const uint64_t* hi, uint64_t* out, size_t G) {
+  return scb_debug_resolve52_geo(ctx, 10, 4, cols, hi, out, G);
 }
 
 extern "C" int scb_fixed_base_load(scb_ctx* ctx, int tslot, int slot, const uint32_t* base, int exp_bits) {

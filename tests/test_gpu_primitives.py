@@ -183,36 +183,61 @@ def test_argument_errors(eng):
     assert eng.modmul(SLOT, np.zeros((0, k), np.uint32), np.zeros((0, k), np.uint32)).shape == (0, k)
 
 
-def test_fp64_engine_carry_resolution_rare_paths(eng):
-    """resolve_carries of the FP64 engine on crafted columns: all-ones digits with a carry arriving from below (the
-    second-order ripple loop, probability ~2^-52 per product on random data), big lane carries, mixed cases."""
-    K, TPI, L = 40, 4, 10
+@pytest.mark.parametrize("L,TPI", [(10, 4), (10, 2), (10, 8), (10, 16), (5, 4), (5, 8), (5, 16), (15, 2), (15, 4), (15, 8)],
+                         ids=lambda v: str(v))
+def test_fp64_engine_carry_resolution_rare_paths(eng, L, TPI):
+    """resolve_carries of the FP64 engine on crafted columns, in every geometry the engine instantiates: all-ones digits
+    with a carry arriving from below (the ripple loop behind the common path: about 2^-46 per lane and product on random
+    data, i.e. it DOES run in production, a few times per day and GPU), big lane carries, carries that stop inside a lane,
+    at a lane boundary, or run through every lane, mixed random cases."""
+    K = L * TPI
     M52 = (1 << 52) - 1
-    rng = random.Random(52)
+    rng = random.Random(52 + 100 * L + TPI)
     cases = []
     ones = [M52] * K
-    cases.append(([1] + [0] * (K - 1), [0] * TPI))                                   # trivial
-    cases.append(([M52 + 1] + ones[1:K - 1] + [0], [0] * TPI))                        # +1 ripples through every lane to the top digit
-    cases.append(([M52 + 5] + ones[1:L] + ones[L:2 * L] + [7] + [0] * (K - 2 * L - 1), [0] * TPI))   # ripple across two lane boundaries
-    cases.append(([(1 << 58) + 3] * (K - 2) + [0, 0], [0] * TPI))                     # large column values everywhere
-    c = list(ones); c[L - 1] = M52; c[0] = M52 + 1; c[K - 1] = 0
-    cases.append((c, [0] * TPI))
-    cases.append(([M52] * (K - 1) + [0], [1, 0, 0, 0]))                                # carry enters through the lane's high accumulator
-    cases.append(([M52] * (K - 1) + [0], [(1 << 57) + 1, 1, 1, 0]))
-    for _ in range(40):
+    zero_hi = [0] * TPI
+    cases.append(([1] + [0] * (K - 1), zero_hi))                                     # trivial
+    cases.append(([M52 + 1] + ones[1:K - 1] + [0], zero_hi))                          # +1 ripples through every lane to the top digit
+    if TPI >= 3:
+        cases.append(([M52 + 5] + ones[1:2 * L] + [7] + [0] * (K - 2 * L - 1), zero_hi))   # ripple across two lane boundaries, stops
+    cases.append(([(1 << 58) + 3] * (K - 2) + [0, 0], zero_hi))                       # large column values everywhere
+    cases.append(([M52 + 1] + ones[1:K - 1] + [0], zero_hi))
+    cases.append(([M52] * (K - 1) + [0], [1] + [0] * (TPI - 1)))                      # carry enters through the lane's high accumulator
+    cases.append(([M52] * (K - 1) + [0], [(1 << 57) + 1] + [1] * (TPI - 2) + [0] if TPI >= 2 else [0]))
+    for stop in range(1, min(K - 1, 2 * L + 2)):                                       # a carry out of digit 0 that dies at digit `stop`
+        c = [M52 + 1] + [M52] * (stop - 1) + [rng.getrandbits(51)] + [rng.getrandbits(52) for _ in range(K - stop - 2)] + [0]
+        cases.append((c[:K], zero_hi))
+    for lane in range(1, TPI):                                                         # digits 0 / 1 of a lane take the neighbour's big carry-out
+        c = [rng.getrandbits(52) for _ in range(K)]
+        c[lane * L - 1] = (1 << 62) + M52
+        c[lane * L] = M52
+        c[lane * L + 1] = M52
+        c[K - 1] = 0
+        if lane * L + 1 == K - 1:
+            c[lane * L] = 0
+        cases.append((c, zero_hi))
+    for _ in range(60):
         cols = [rng.choice([M52, M52, M52 + 1, rng.getrandbits(60), 0, 1]) for _ in range(K - 1)] + [0]
         hi = [rng.choice([0, 1, rng.getrandbits(56)]) for _ in range(TPI - 1)] + [0]
         cases.append((cols, hi))
-    G = len(cases)
-    cols = np.array([c for c, _ in cases], dtype=np.uint64)
-    hi = np.array([h for _, h in cases], dtype=np.uint64)
-    out = np.zeros((G, K), dtype=np.uint64)
-    eng._check(eng.lib.scb_debug_resolve52(eng.ctx, nat._ptr(cols), nat._ptr(hi), nat._ptr(out), G))
-    for (c, h), digits in zip(cases, out.tolist()):
+    kept = []
+    for c, h in cases:
         value = sum(int(v) << (52 * i) for i, v in enumerate(c)) + sum(int(v) << (52 * L * (t + 1)) for t, v in enumerate(h))
-        assert value < 1 << (52 * K), "test case overflows the representation"
+        if value < 1 << (52 * K):                                                      # must fit K digits
+            kept.append((c, h, value))
+    assert len(kept) >= 40
+    G = len(kept)
+    cols = np.array([c for c, _, _ in kept], dtype=np.uint64)
+    hi = np.array([h for _, h, _ in kept], dtype=np.uint64)
+    out = np.zeros((G, K), dtype=np.uint64)
+    eng._check(eng.lib.scb_debug_resolve52_geo(eng.ctx, L, TPI, nat._ptr(cols), nat._ptr(hi), nat._ptr(out), G))
+    for (c, h, value), digits in zip(kept, out.tolist()):
         assert all(d <= M52 for d in digits)
         assert sum(d << (52 * i) for i, d in enumerate(digits)) == value
+    if (L, TPI) == (10, 4):                                                            # the fixed-geometry entry point is the same code
+        out2 = np.zeros((G, K), dtype=np.uint64)
+        eng._check(eng.lib.scb_debug_resolve52(eng.ctx, nat._ptr(cols), nat._ptr(hi), nat._ptr(out2), G))
+        assert np.array_equal(out, out2)
 
 
 @pytest.mark.parametrize("fp64", [True, False], ids=["fp64", "imad"])
