@@ -91,7 +91,10 @@ __device__ __forceinline__ void resolve_carries(uint64_t (&col)[L], uint64_t hi_
   // lane and product on random data), so the common case ends here; the loop ripples it through the rest of the lane, then
   // lane by lane from digit 0 (warp-uniform trip count; driven by test_fp64_engine_carry_resolution_rare_paths).
   // Measured at B = 65,536 against an unconditional second sweep: 1.0-1.5 % on every exponentiation kernel; a carry-save
-  // first step (all columns split at once, depth independent of L) measured 0.5-2 % slower than this form.
+  // first step (all columns split at once, depth independent of L) measured 0.5-2 % slower than this form.  (The plain
+  // 1024-bit launches of 3 x 65,536 elements are the exception when timed ALONE -- 54.2 ms with the full sweep, 56.6 ms with
+  // this form -- but inside a pass, where the other CRT chain runs next to them, this form wins: 988.6 against 990.5 ms per
+  // pass; profiles/r02_resolve_plain.log.)
   int from = 2;
   while (__any_sync(FULL, k != 0)) {
 #pragma unroll
