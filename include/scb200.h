@@ -170,8 +170,10 @@ enum {
                                    either way; the 52-bit fixed-base tables are built when the DGK key is loaded with the option on) */
   SCB_OPT_SMALL_BATCH = 6,      /* FP64 engine: batches that cannot fill half of the GPU's resident groups run with 5 digits per lane on
                                    twice as many lanes per number (default 1; results are bit-identical either way) */
-  SCB_OPT_OVERLAP_CRT = 7,      /* the p and q halves of the KeyHolder's CRT forms on two streams, so that one half's launches fill the
-                                   SMs the other's draining launch gives back (default 1; off while scb_profile_begin is active) */
+  SCB_OPT_OVERLAP_CRT = 7,      /* independent launch chains inside one call on two streams of the context -- the p and q halves of
+                                   the KeyHolder's CRT forms; the Initiator's rho^N next to the batched inversion of step 1 -- so
+                                   that one chain fills the SMs the other's draining launch gives back (default 1; off while
+                                   scb_profile_begin is active; results are bit-identical either way) */
   SCB_OPT_SQUARE_MODULUS = 5    /* exponentiations modulo a linked square n^2 (N^2, p^2, q^2: scb_modulus_link_square) in base-n pair
                                    form on the FP64 engine: half the digit products of a plain product mod n^2 (default 1; 0 = treat
                                    n^2 as an ordinary modulus; results are bit-identical either way) */

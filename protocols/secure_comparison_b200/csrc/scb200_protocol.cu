@@ -590,6 +590,51 @@ extern "C" int scb_paillier_set_private_crt(scb_ctx* ctx, const uint32_t* p, con
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// The launches issued while an AuxLane is alive go to the context's second stream (with their own per-group scratch), ordered
+// after everything the main stream held when fork() was called; the destructor makes the main stream wait for them.  Used
+// for the q half of the CRT forms below: the p and q chains are independent, and a launch of one chain fills the SMs that a
+// draining launch of the other gives back (the last tickets of an exponentiation launch otherwise finish on a mostly idle
+// GPU).  Off while per-kernel timing is on (one event stream) and with SCB_OPT_OVERLAP_CRT = 0.
+struct AuxLane {
+  scb_ctx* ctx;
+  bool on = false;
+  bool join_on_exit = true;
+  static bool fork(scb_ctx* ctx) {
+    if (!ctx->use_overlap || ctx->profiling) return false;
+    if (!ctx->aux_stream) {
+      cudaStream_t st = nullptr;
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+        if (st) cudaStreamDestroy(st);
+        if (a) cudaEventDestroy(a);
+        cudaGetLastError();
+        return false;
+      }
+      ctx->aux_stream = st;
+      ctx->ev_fork = a;
+      ctx->ev_join = b;
+    }
+    return cudaEventRecord(ctx->ev_fork, ctx->stream) == cudaSuccess && cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0) == cudaSuccess;
+  }
+  // join_on_exit = false: the caller issues more main-stream work that may overlap and calls join() itself
+  AuxLane(scb_ctx* c, bool forked, bool join_at_exit = true) : ctx(c), on(forked), join_on_exit(join_at_exit) {
+    if (!on) return;
+    std::swap(ctx->stream, ctx->aux_stream);
+    ctx->on_aux = true;
+  }
+  ~AuxLane() {
+    if (!on) return;
+    std::swap(ctx->stream, ctx->aux_stream);
+    ctx->on_aux = false;
+    if (join_on_exit) join(ctx);
+  }
+  static void join(scb_ctx* ctx) {
+    cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+  }
+};
+
 template <int L, int TPI>
 int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32_t* r, const uint32_t* rho, int l, uint32_t* out, size_t B) {
   using C = Cfg<L, TPI>;
@@ -600,23 +645,34 @@ int phase_step1(scb_ctx* ctx, const uint32_t* x, const uint32_t* y, const uint32
   if (rc) return rc;
   uint32_t* xinv = dg.take<uint32_t>(B * C::K);
   uint8_t* ok = dg.take<uint8_t>(B);
-  bool any_fail = false;
-  rc = batch_modinv_mont<L, TPI>(ctx, SCB_MOD_PAILLIER_N2, x, B, xinv, ok, &any_fail);
-  if (rc) return rc;
   const int ebits = md.bits > 0 ? ctx->mod[SCB_MOD_PAILLIER_N].bits : 0;
   const int wbits = window_bits_for(ebits);
-  // the randomizer rho^N mod N^2 on the FP64 engine when it is enabled: a separate launch, then k_step1 only multiplies
+  // the randomizer rho^N mod N^2 on the FP64 engine when it is enabled: a separate launch, then k_step1 only multiplies.
+  // It does not depend on x^-1, so it goes to the second stream FIRST and the (latency-bound, nearly empty) kernels of the
+  // batched inversion move into the SMs its drain phase gives back; k_step1 waits for both.
   const uint32_t* rho_pow = nullptr;
+  bool forked = false;
   if (rho != nullptr && ctx->use_f64 && md.K52 > 0) {
     Arena rp;
     rc = get_arena(ctx, SC_CRT, pad256(sizeof(uint32_t) * B * 2 * kN), &rp);
     if (rc) return rc;
     uint32_t* pw = rp.take<uint32_t>(B * 2 * kN);
-    rc = scb::modexp_any(ctx, SCB_MOD_PAILLIER_N2, rho, kN, keys_N_words(ctx), kN, 0, ebits, nullptr, pw, 2 * kN, B);
-    if (rc) return rc;
+    forked = AuxLane::fork(ctx);
+    {
+      AuxLane lane(ctx, forked, false);
+      rc = scb::modexp_any(ctx, SCB_MOD_PAILLIER_N2, rho, kN, keys_N_words(ctx), kN, 0, ebits, nullptr, pw, 2 * kN, B);
+    }
+    if (rc) {
+      if (forked) AuxLane::join(ctx);
+      return rc;
+    }
     rho_pow = pw;
     rho = nullptr;
   }
+  bool any_fail = false;
+  rc = batch_modinv_mont<L, TPI>(ctx, SCB_MOD_PAILLIER_N2, x, B, xinv, ok, &any_fail);
+  if (forked) AuxLane::join(ctx);
+  if (rc) return rc;
   int wb = wbits, nprog = 0, pw = 0;
   const uint16_t* prog = ctx->find_program(keys_N_words(ctx), &nprog, &pw, &wb);    // IMAD engine: sliding-window program of N
   const int grid = ctx->grid_for(reinterpret_cast<const void*>(&k_step1<L, TPI>), C::SMEM, B, C::GPB);
@@ -946,46 +1002,6 @@ int phase_crt_decrypt_combine(scb_ctx* ctx, const uint32_t* Lq, uint32_t* out, s
   k_crt_decrypt_combine<L, TPI><<<grid, BLOCK_THREADS, C::SMEM, ctx->stream>>>(md.dev, ctx->keys_dev, Lq, static_cast<uint32_t*>(scratch), out, M);
   return ctx->launched("k_crt_decrypt_combine");
 }
-
-// The launches issued while an AuxLane is alive go to the context's second stream (with their own per-group scratch), ordered
-// after everything the main stream held when fork() was called; the destructor makes the main stream wait for them.  Used
-// for the q half of the CRT forms below: the p and q chains are independent, and a launch of one chain fills the SMs that a
-// draining launch of the other gives back (the last tickets of an exponentiation launch otherwise finish on a mostly idle
-// GPU).  Off while per-kernel timing is on (one event stream) and with SCB_OPT_OVERLAP_CRT = 0.
-struct AuxLane {
-  scb_ctx* ctx;
-  bool on = false;
-  static bool fork(scb_ctx* ctx) {
-    if (!ctx->use_overlap || ctx->profiling) return false;
-    if (!ctx->aux_stream) {
-      cudaStream_t st = nullptr;
-      cudaEvent_t a = nullptr, b = nullptr;
-      if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
-        if (st) cudaStreamDestroy(st);
-        if (a) cudaEventDestroy(a);
-        cudaGetLastError();
-        return false;
-      }
-      ctx->aux_stream = st;
-      ctx->ev_fork = a;
-      ctx->ev_join = b;
-    }
-    return cudaEventRecord(ctx->ev_fork, ctx->stream) == cudaSuccess && cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0) == cudaSuccess;
-  }
-  AuxLane(scb_ctx* c, bool forked) : ctx(c), on(forked) {
-    if (!on) return;
-    std::swap(ctx->stream, ctx->aux_stream);
-    ctx->on_aux = true;
-  }
-  ~AuxLane() {
-    if (!on) return;
-    std::swap(ctx->stream, ctx->aux_stream);
-    ctx->on_aux = false;
-    cudaEventRecord(ctx->ev_join, ctx->aux_stream);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-  }
-};
 
 // KeyHolder with the factorisation: (1 + m N) * rho^N mod N^2 through p, p^2, q, q^2 (see kernels_protocol.cuh)
 int paillier_encrypt_crt(scb_ctx* ctx, const uint32_t* plain, const uint32_t* rho, uint32_t* out, size_t M) {
