@@ -120,10 +120,15 @@ def test_step1_pieces(setup):
     want = [oracle.step_1(a, b, l, c) for a, b, c in zip(x, y, r)]
     bad = [i for i in range(B) if got[i] != want[i]]
     assert not bad, f"step_1 without randomize differs at {bad[:10]}"
-    got = limbs_to_ints(eng.initiator_step1(X, Y, R, RHO, l))
     want = [oracle.paillier_randomize(oracle.step_1(a, b, l, c), d) for a, b, c, d in zip(x, y, r, rho)]
-    bad = [i for i in range(B) if got[i] != want[i]]
-    assert not bad, f"step_1 + randomize differs at {bad[:10]}"
+    try:
+        for overlap in (True, False, True):          # rho^N on the second stream next to the inversion of x, or one stream
+            eng.set_overlap_crt(overlap)
+            got = limbs_to_ints(eng.initiator_step1(X, Y, R, RHO, l))
+            bad = [i for i in range(B) if got[i] != want[i]]
+            assert not bad, f"step_1 + randomize (two streams: {overlap}) differs at {bad[:10]}"
+    finally:
+        eng.set_overlap_crt(True)
 
 
 def test_dgk_bit_encryption(setup):
